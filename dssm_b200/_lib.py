@@ -1,0 +1,134 @@
+"""ctypes binding of libdssm_b200.so (include/dssm_b200.h).
+
+There is no CPU fallback: if the library is missing and cannot be built with nvcc, importing this module
+raises.  PyTorch tensors are used only as device buffers -- every call passes raw pointers and sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libdssm_b200.so"
+
+DSSM_OK = 0
+ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
+GEMM = {"fp32": 0, "bf16_tc": 1}
+MAX_LAYERS = 8
+
+
+class DssmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dssm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class dssm_config(C.Structure):
+    _fields_ = [
+        ("TRIGRAM_D", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("layers", C.c_int32 * MAX_LAYERS),
+        ("NEG", C.c_int32),
+        ("query_BS", C.c_int32),
+        ("use_bn", C.c_int32),
+        ("act", C.c_int32),
+        ("loss_div_bs", C.c_int32),
+        ("gemm_mode", C.c_int32),
+        ("bn_eps", C.c_float),
+        ("ema_decay", C.c_float),
+        ("gamma", C.c_float),
+        ("loss_eps", C.c_float),
+        ("learning_rate", C.c_float),
+        ("beta1", C.c_float),
+        ("beta2", C.c_float),
+        ("adam_eps", C.c_float),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists() or os.environ.get("DSSM_B200_REBUILD") == "1":
+        from .build import build  # needs nvcc; raises if absent
+
+        build(force=os.environ.get("DSSM_B200_REBUILD") == "1")
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing and could not be built; dssm_b200 has no CPU fallback")
+    return C.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+_p, _i32, _i64, _f, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dssm_b200.h one to one
+SIGNATURES = {
+    "dssm_last_error": (C.c_char_p, []),
+    "dssm_version": (C.c_int, []),
+    "dssm_sm_count": (C.c_int, []),
+    "dssm_spmm_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p]),
+    "dssm_spmm_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64]),
+    "dssm_spmm_bwd_dw": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
+    "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
+    "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
+    "dssm_bn_act_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "dssm_fc_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p]),
+    "dssm_fc_bwd_dx": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p]),
+    "dssm_fc_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dssm_fc_bwd_dw": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _i32, _p, _sz, _p]),
+    "dssm_colsum_workspace_bytes": (_sz, [_i32, _i32]),
+    "dssm_colsum": (C.c_int, [_p, _i32, _i32, _p, _p, _sz, _p]),
+    "dssm_merge_negative_doc": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "dssm_merge_negative_doc_index": (C.c_int, [_i32, _i32, _p, _p]),
+    "dssm_cos_softmax_loss": (C.c_int, [_p, _i32, _i32, _i32, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dssm_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
+    "dssm_adam_advance": (C.c_int, [_p, _f, _f, _p]),
+    "dssm_corpus_topk_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
+    "dssm_corpus_topk": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "dssm_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "dssm_tower_create": (C.c_int, [C.POINTER(dssm_config), C.POINTER(_p)]),
+    "dssm_tower_destroy": (None, [_p]),
+    "dssm_tower_param_count": (_i64, [_p]),
+    "dssm_tower_ema_count": (_i64, [_p]),
+    "dssm_tower_workspace_bytes": (_sz, [_p, _i64]),
+    "dssm_tower_num_tensors": (_i32, [_p, _i32]),
+    "dssm_tower_tensor_info": (C.c_int, [_p, _i32, _i32, C.c_char_p, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "dssm_tower_bind": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64]),
+    "dssm_tower_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p]),
+    "dssm_tower_backward": (C.c_int, [_p, _p]),
+    "dssm_tower_adam": (C.c_int, [_p, _f, _p]),
+    "dssm_tower_train_step": (C.c_int, [_p, _p, _p, _p, _p]),
+    "dssm_tower_train_step_host": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "dssm_tower_capture_graph": (C.c_int, [_p, _p]),
+    "dssm_tower_staging": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "dssm_tower_train_step_staged": (C.c_int, [_p, _p]),
+    "dssm_tower_launch_count": (_i64, [_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.dssm_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != DSSM_OK:
+        raise DssmError(rc, last_error())
+
+
+def ptr(t) -> int:
+    """Device (or pinned host) pointer of a torch tensor / None."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(stream=None) -> int:
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream

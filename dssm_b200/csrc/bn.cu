@@ -1,0 +1,292 @@
+// batch_normalization (new_dssm.py:62-88) for the two instances of one layer (query rows [0,B), doc rows
+// [B,R)), its EMA update, the fused normalise+activation, and the backward through act(BN(x)).
+//
+// Moments are computed two-pass per row chunk (chunk mean, then centred sum of squares) and the chunk
+// triples (n, mean, M2) are merged in chunk order with Chan's formula -- no E[x^2]-E[x]^2 cancellation, and
+// the result does not depend on the launch geometry.  Reductions across rows use warp shuffles.
+#include "common.cuh"
+
+namespace dssm {
+
+constexpr int BN_CHUNK_ROWS = 256;  // rows per partial
+constexpr int BN_TX = 32;           // columns per block
+constexpr int BN_TY = 8;            // row lanes per block
+
+// chunk table: chunks never straddle the segment boundary
+__host__ __device__ inline int bn_chunks_of(int rows) { return (rows + BN_CHUNK_ROWS - 1) / BN_CHUNK_ROWS; }
+
+// partial layout: [3][n_chunks_total][L]  (count as float, mean, M2)
+__global__ void __launch_bounds__(BN_TX * BN_TY)
+bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total) {
+    __shared__ float red[BN_TY][BN_TX + 1];
+    __shared__ float s_mean[BN_TX];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int col = blockIdx.x * BN_TX + tx;
+    const int nq = bn_chunks_of(B);
+    int chunk = blockIdx.y, r0, r1;
+    if (chunk < nq) {
+        r0 = chunk * BN_CHUNK_ROWS;
+        r1 = min(B, r0 + BN_CHUNK_ROWS);
+    } else {
+        r0 = B + (chunk - nq) * BN_CHUNK_ROWS;
+        r1 = min(R, r0 + BN_CHUNK_ROWS);
+    }
+    const int n = r1 - r0;
+    float s = 0.f;
+    if (col < L)
+        for (int r = r0 + ty; r < r1; r += BN_TY) s += __ldg(X + (size_t)r * L + col);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN_TY; ++i) t += red[i][tx];
+        s_mean[tx] = t / (float)n;
+    }
+    __syncthreads();
+    const float mu = s_mean[tx];
+    float q = 0.f;
+    if (col < L)
+        for (int r = r0 + ty; r < r1; r += BN_TY) {
+            const float d = __ldg(X + (size_t)r * L + col) - mu;
+            q = fmaf(d, d, q);
+        }
+    __syncthreads();
+    red[ty][tx] = q;
+    __syncthreads();
+    if (ty == 0 && col < L) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN_TY; ++i) t += red[i][tx];
+        part[((size_t)0 * n_chunks_total + chunk) * L + col] = (float)n;
+        part[((size_t)1 * n_chunks_total + chunk) * L + col] = mu;
+        part[((size_t)2 * n_chunks_total + chunk) * L + col] = t;
+    }
+}
+
+// one thread per (segment, column): merge chunk partials in order, EMA, scale/shift
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L,
+                                   int on_train, int update_ema, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ ema_mean,
+                                   float* __restrict__ ema_var, float eps, float decay, float* __restrict__ mean_o,
+                                   float* __restrict__ var_o, float* __restrict__ rstd_o, float* __restrict__ scale_o,
+                                   float* __restrict__ shift_o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * L) return;
+    const int seg = i / L, col = i - seg * L;
+    float mean, var;
+    if (on_train) {
+        const int c0 = seg == 0 ? 0 : nq_chunks;
+        const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
+        if (c0 == c1) return;  // empty segment (single-instance call, B == R)
+        float n = 0.f, mu = 0.f, m2 = 0.f;
+        for (int c = c0; c < c1; ++c) {
+            const float nb = part[((size_t)0 * n_chunks_total + c) * L + col];
+            const float mb = part[((size_t)1 * n_chunks_total + c) * L + col];
+            const float qb = part[((size_t)2 * n_chunks_total + c) * L + col];
+            const float nt = n + nb;
+            const float delta = mb - mu;
+            mu = mu + delta * (nb / nt);
+            m2 = m2 + qb + delta * delta * (n * nb / nt);
+            n = nt;
+        }
+        mean = mu;
+        var = m2 / n;  // biased (tf.nn.moments)
+        if (update_ema) {
+            // ExponentialMovingAverage.apply: shadow -= (1 - decay) * (shadow - value), new_dssm.py:78-81
+            const float em = ema_mean[i], ev = ema_var[i];
+            ema_mean[i] = em - (1.f - decay) * (em - mean);
+            ema_var[i] = ev - (1.f - decay) * (ev - var);
+        }
+    } else {
+        mean = ema_mean[i];
+        var = ema_var[i];
+    }
+    const float rstd = 1.0f / sqrtf(var + eps);
+    const float sc = rstd * gamma[i];
+    mean_o[i] = mean;
+    var_o[i] = var;
+    rstd_o[i] = rstd;
+    scale_o[i] = sc;
+    shift_o[i] = beta[i] - mean * sc;
+}
+
+__global__ void bn_act_apply_kernel(const float* __restrict__ X, int R, int L, int B, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int act, float* __restrict__ Y) {
+    const size_t total = (size_t)R * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / L), c = (int)(i - (size_t)r * L);
+        float x = __ldg(X + i);
+        if (scale) {
+            const int o = (r < B ? 0 : L) + c;
+            x = fmaf(x, __ldg(scale + o), __ldg(shift + o));
+        }
+        Y[i] = act_fwd(x, act);
+    }
+}
+
+// ---- backward -------------------------------------------------------------------------------------
+// pass 1: per chunk column sums of g = dA*act'(a) and g*xhat  -> part [2][n_chunks_total][L]
+__global__ void __launch_bounds__(BN_TX * BN_TY)
+bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                     const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total) {
+    __shared__ float red0[BN_TY][BN_TX + 1];
+    __shared__ float red1[BN_TY][BN_TX + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int col = blockIdx.x * BN_TX + tx;
+    const int nq = bn_chunks_of(B);
+    int chunk = blockIdx.y, r0, r1, seg;
+    if (chunk < nq) {
+        seg = 0; r0 = chunk * BN_CHUNK_ROWS; r1 = min(B, r0 + BN_CHUNK_ROWS);
+    } else {
+        seg = 1; r0 = B + (chunk - nq) * BN_CHUNK_ROWS; r1 = min(R, r0 + BN_CHUNK_ROWS);
+    }
+    float sg = 0.f, sgx = 0.f;
+    if (col < L) {
+        const int o = seg * L + col;
+        const float mu = __ldg(mean + o), rs = __ldg(rstd + o), sc = __ldg(scale + o), sh = __ldg(shift + o);
+        for (int r = r0 + ty; r < r1; r += BN_TY) {
+            const float h = __ldg(H + (size_t)r * L + col);
+            const float a = act_fwd(fmaf(h, sc, sh), act);
+            const float g = __ldg(dA + (size_t)r * L + col) * act_grad_from_out(a, act);
+            sg += g;
+            sgx = fmaf(g, (h - mu) * rs, sgx);
+        }
+    }
+    red0[ty][tx] = sg;
+    red1[ty][tx] = sgx;
+    __syncthreads();
+    if (ty == 0 && col < L) {
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN_TY; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
+        part[((size_t)0 * n_chunks_total + chunk) * L + col] = t0;
+        part[((size_t)1 * n_chunks_total + chunk) * L + col] = t1;
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * L) return;
+    const int seg = i / L, col = i - seg * L;
+    const int c0 = seg == 0 ? 0 : nq_chunks;
+    const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
+    float b = 0.f, g = 0.f;
+    for (int c = c0; c < c1; ++c) {
+        b += part[((size_t)0 * n_chunks_total + c) * L + col];
+        g += part[((size_t)1 * n_chunks_total + c) * L + col];
+    }
+    dbeta[i] = b;
+    dgamma[i] = g;
+}
+
+// pass 2 (in place): dH = gamma*rstd * (g - dbeta/n - xhat*dgamma/n)
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta) {
+    const size_t total = (size_t)R * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / L), c = (int)(i - (size_t)r * L);
+        const int seg = r < B ? 0 : 1;
+        const int o = seg * L + c;
+        const float n = seg == 0 ? (float)B : (float)(R - B);
+        const float h = __ldg(H + i);
+        const float a = act_fwd(fmaf(h, __ldg(scale + o), __ldg(shift + o)), act);
+        const float g = dA[i] * act_grad_from_out(a, act);
+        const float rs = __ldg(rstd + o);
+        const float xhat = (h - __ldg(mean + o)) * rs;
+        dA[i] = (__ldg(gamma + o) * rs) * (g - __ldg(dbeta + o) / n - xhat * (__ldg(dgamma + o) / n));
+    }
+}
+
+// no-BN mode: dH = dA * act'(act(H))
+__global__ void act_bwd_kernel(float* __restrict__ dA, const float* __restrict__ H, size_t total, int act) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = act_fwd(__ldg(H + i), act);
+        dA[i] = dA[i] * act_grad_from_out(a, act);
+    }
+}
+
+static int ew_blocks(size_t total) {
+    size_t b = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace dssm
+
+using namespace dssm;
+
+extern "C" size_t dssm_bn_workspace_bytes(int32_t R, int32_t L) {
+    if (R <= 0 || L <= 0) return 0;
+    // worst case split of R rows into two segments adds one chunk
+    const size_t chunks = (size_t)bn_chunks_of(R) + 2;
+    return align_up(3 * chunks * (size_t)L * sizeof(float), 256);
+}
+
+extern "C" int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, int32_t on_train, int32_t update_ema,
+                               const float* gamma, const float* beta, float* ema_mean, float* ema_var, float eps,
+                               float ema_decay, float* mean, float* var, float* rstd, float* scale, float* shift,
+                               void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(X && gamma && beta && ema_mean && ema_var && mean && var && rstd && scale && shift, DSSM_ERR_BAD_ARG,
+                 "dssm_bn_forward: null pointer");
+    DSSM_REQUIRE(R > 0 && L > 0 && B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_forward: need 0 < B <= R (R=%d B=%d)", R, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nq = bn_chunks_of(B), nd = bn_chunks_of(R - B), nt = nq + nd;
+    float* part = (float*)workspace;
+    if (on_train) {
+        DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
+                     "dssm_bn_forward: workspace too small");
+        dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
+        bn_stats_kernel<<<grid, block, 0, st>>>(X, R, L, B, part, nt);
+        LAUNCH_CHECK("bn_stats");
+    }
+    bn_finalize_kernel<<<cdiv(2 * L, 128), 128, 0, st>>>(part, nt, nq, L, on_train, update_ema, gamma, beta, ema_mean,
+                                                         ema_var, eps, ema_decay, mean, var, rstd, scale, shift);
+    LAUNCH_CHECK("bn_finalize");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B, const float* scale,
+                                 const float* shift, int32_t act, float* Y, dssm_stream_t stream) {
+    DSSM_REQUIRE(X && Y, DSSM_ERR_BAD_ARG, "dssm_bn_act_apply: null pointer");
+    DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_bn_act_apply: scale/shift must both be set or both NULL");
+    DSSM_REQUIRE(R >= 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_apply: bad shape");
+    if (R == 0) return DSSM_OK;
+    bn_act_apply_kernel<<<ew_blocks((size_t)R * L), 256, 0, (cudaStream_t)stream>>>(X, R, L, B, scale, shift, act, Y);
+    LAUNCH_CHECK("bn_act_apply");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act,
+                                    const float* gamma, const float* mean, const float* rstd, const float* scale,
+                                    const float* shift, float* dgamma, float* dbeta, void* workspace,
+                                    size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(dA && H, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null pointer");
+    DSSM_REQUIRE(R > 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!scale) {
+        act_bwd_kernel<<<ew_blocks((size_t)R * L), 256, 0, st>>>(dA, H, (size_t)R * L, act);
+        LAUNCH_CHECK("act_bwd");
+        return DSSM_OK;
+    }
+    DSSM_REQUIRE(gamma && mean && rstd && shift && dgamma && dbeta, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null BN pointer");
+    DSSM_REQUIRE(B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
+    const int nq = bn_chunks_of(B), nd = bn_chunks_of(R - B), nt = nq + nd;
+    DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)2 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
+                 "dssm_bn_act_backward: workspace too small");
+    float* part = (float*)workspace;
+    dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
+    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt);
+    LAUNCH_CHECK("bn_bwd_reduce");
+    bn_bwd_finalize_kernel<<<cdiv(2 * L, 128), 128, 0, st>>>(part, nt, nq, L, dgamma, dbeta);
+    LAUNCH_CHECK("bn_bwd_finalize");
+    bn_bwd_apply_kernel<<<ew_blocks((size_t)R * L), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift,
+                                                                 dgamma, dbeta);
+    LAUNCH_CHECK("bn_bwd_apply");
+    return DSSM_OK;
+}

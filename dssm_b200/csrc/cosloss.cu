@@ -1,0 +1,207 @@
+// Merge_Negative_Doc (new_dssm.py:160-180), Cosine_Similarity (:182-201) and Loss (:203-213) with the
+// gradient w.r.t. the embeddings, one warp per query group.  The merge is never materialised on the
+// training path: group j reads its positive at row B+j and negative slot i at row 2B + j*NEG + i, which
+// is exactly doc_y[(i+1)*B + j] of the reference's concat chain.  The standalone gather kernel and its
+// index form exist for callers that want doc_y itself (and for the bit-exact ordering test).
+#include "common.cuh"
+#include <math.h>
+
+namespace dssm {
+
+constexpr int CL_WARPS = 4;
+
+// dynamic smem per warp: 3*(1+NEG) floats (dot, dnorm, coefficient)
+__global__ void __launch_bounds__(CL_WARPS * 32)
+cos_softmax_loss_kernel(const float* __restrict__ Y, int B, int NEG, int L, float gamma, float loss_eps, float inv_denom,
+                        float* __restrict__ query_norm_single, float* __restrict__ doc_norm,
+                        float* __restrict__ cos_sim_raw, float* __restrict__ cos_sim, float* __restrict__ prob,
+                        float* __restrict__ loss_terms, float* __restrict__ dY) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int K1 = NEG + 1;
+    float* s_dot = smem + (size_t)w * 3 * K1;
+    float* s_dn = s_dot + K1;
+    float* s_c = s_dn + K1;
+    const int j = blockIdx.x * CL_WARPS + w;
+    if (j >= B) return;
+    const float* q = Y + (size_t)j * L;
+    // ||q||
+    float qq = 0.f;
+    for (int c = lane; c < L; c += 32) {
+        const float x = __ldg(q + c);
+        qq = fmaf(x, x, qq);
+    }
+    qq = warp_sum(qq);
+    const float qn = sqrtf(qq);
+    // dots and doc norms
+    for (int k = 0; k < K1; ++k) {
+        const size_t drow = (k == 0) ? (size_t)(B + j) : (size_t)(2 * B) + (size_t)j * NEG + (k - 1);
+        const float* d = Y + drow * L;
+        float dd = 0.f, dq = 0.f;
+        for (int c = lane; c < L; c += 32) {
+            const float x = __ldg(d + c);
+            dd = fmaf(x, x, dd);
+            dq = fmaf(x, __ldg(q + c), dq);
+        }
+        dd = warp_sum(dd);
+        dq = warp_sum(dq);
+        if (lane == 0) {
+            s_dot[k] = dq;
+            s_dn[k] = sqrtf(dd);
+        }
+    }
+    __syncwarp();
+    // softmax over the 1+NEG logits (lanes stride over k)
+    float mx = -INFINITY;
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_dot[k] / (qn * s_dn[k]);  // tf.truediv, no epsilon: 0/0 = NaN
+        mx = fmaxf(mx, raw * gamma);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_dot[k] / (qn * s_dn[k]);
+        se += expf(raw * gamma - mx);
+    }
+    se = warp_sum(se);
+    const float raw0 = s_dot[0] / (qn * s_dn[0]);
+    const float p0 = expf(raw0 * gamma - mx) / se;
+    // NaN anywhere in the group poisons the softmax exactly as in TF (max/exp/sum propagate NaN);
+    // fmaxf drops NaNs, so re-inject: if any logit is NaN the sum must be NaN.
+    float any_nan = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_dot[k] / (qn * s_dn[k]);
+        if (raw != raw) any_nan = 1.f;
+    }
+    any_nan = warp_sum(any_nan);
+    const float poison = any_nan > 0.f ? NAN : 0.f;
+    const float wgt = p0 / (p0 + loss_eps);
+    float sum_c_raw = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_dot[k] / (qn * s_dn[k]);
+        const float logit = raw * gamma;
+        const float p = expf(logit - mx) / se + poison;
+        if (cos_sim_raw) cos_sim_raw[(size_t)k * B + j] = raw;
+        if (doc_norm) doc_norm[(size_t)k * B + j] = s_dn[k];
+        if (cos_sim) cos_sim[(size_t)j * K1 + k] = logit;
+        if (prob) prob[(size_t)j * K1 + k] = p;
+        // dLoss/dcos_k = gamma * w * (p_k - [k==0]) / denom
+        const float dcos = gamma * (wgt * (p - (k == 0 ? 1.f : 0.f)) * inv_denom);
+        s_c[k] = dcos;
+        sum_c_raw = fmaf(dcos, raw, sum_c_raw);
+    }
+    sum_c_raw = warp_sum(sum_c_raw);
+    if (lane == 0) {
+        if (query_norm_single) query_norm_single[j] = qn;
+        loss_terms[j] = -logf(p0 + poison + loss_eps);
+    }
+    if (!dY) return;
+    __syncwarp();
+    // dq = sum_k c_k/(qn*dn_k) * d_k - (sum_k c_k raw_k)/qn^2 * q ;  dd_k = c_k/(qn*dn_k) * q - c_k raw_k/dn_k^2 * d_k
+    const float qcoef = sum_c_raw / (qn * qn);
+    for (int c = lane; c < L; c += 32) {
+        const float qv = __ldg(q + c);
+        float dqv = 0.f;
+        for (int k = 0; k < K1; ++k) {
+            const size_t drow = (k == 0) ? (size_t)(B + j) : (size_t)(2 * B) + (size_t)j * NEG + (k - 1);
+            const float dv = __ldg(Y + drow * L + c);
+            const float ck = s_c[k], dn = s_dn[k];
+            const float inv_qd = 1.f / (qn * dn);
+            const float raw = s_dot[k] * inv_qd;
+            dqv = fmaf(ck * inv_qd, dv, dqv);
+            dY[drow * L + c] = (ck * inv_qd) * qv - (ck * raw / (dn * dn)) * dv;
+        }
+        dY[(size_t)j * L + c] = dqv - qcoef * qv;
+    }
+}
+
+// loss = sum_j terms[j] * inv_denom, single block, fixed tree
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ terms, int B, float inv_denom,
+                                                            float* __restrict__ loss) {
+    __shared__ float s[1024];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < B; i += 1024) a += terms[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = s[0] * inv_denom;
+}
+
+__global__ void merge_negative_doc_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int B, int NEG,
+                                          int L, float* __restrict__ doc_y) {
+    const size_t total = (size_t)(1 + NEG) * B * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / L;
+        const int c = (int)(i - r * L);
+        float v;
+        if (r < (size_t)B) {
+            v = __ldg(pos + r * L + c);
+        } else {
+            const size_t t = r - B;              // t = i_slot*B + j
+            const size_t slot = t / B, j = t - slot * B;
+            v = __ldg(neg + (j * NEG + slot) * L + c);
+        }
+        doc_y[i] = v;
+    }
+}
+
+__global__ void merge_negative_doc_index_kernel(int B, int NEG, int* __restrict__ src) {
+    const int total = (1 + NEG) * B;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += gridDim.x * blockDim.x) {
+        if (r < B) {
+            src[r] = r;
+        } else {
+            const int t = r - B, slot = t / B, j = t - slot * B;
+            src[r] = B + j * NEG + slot;
+        }
+    }
+}
+
+}  // namespace dssm
+
+using namespace dssm;
+
+extern "C" int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int32_t L, float gamma, float loss_eps,
+                                     int32_t loss_div_bs, float* query_norm_single, float* doc_norm, float* cos_sim_raw,
+                                     float* cos_sim, float* prob, float* loss_terms, float* loss, float* dY,
+                                     dssm_stream_t stream) {
+    DSSM_REQUIRE(Y && loss_terms, DSSM_ERR_BAD_ARG, "dssm_cos_softmax_loss: null pointer");
+    DSSM_REQUIRE(B > 0 && NEG > 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_cos_softmax_loss: bad shape B=%d NEG=%d L=%d", B, NEG, L);
+    const size_t smem = (size_t)CL_WARPS * 3 * (NEG + 1) * sizeof(float);
+    DSSM_REQUIRE(smem <= 48 * 1024, DSSM_ERR_BAD_SHAPE, "dssm_cos_softmax_loss: NEG=%d too large", NEG);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv_denom = loss_div_bs ? 1.0f / (float)B : 1.0f;
+    cos_softmax_loss_kernel<<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(Y, B, NEG, L, gamma, loss_eps, inv_denom,
+                                                                            query_norm_single, doc_norm, cos_sim_raw,
+                                                                            cos_sim, prob, loss_terms, dY);
+    LAUNCH_CHECK("cos_softmax_loss");
+    if (loss) {
+        loss_reduce_kernel<<<1, 1024, 0, st>>>(loss_terms, B, inv_denom, loss);
+        LAUNCH_CHECK("loss_reduce");
+    }
+    return DSSM_OK;
+}
+
+extern "C" int dssm_merge_negative_doc(const float* doc_positive_y, const float* doc_negative_y, int32_t B, int32_t NEG,
+                                       int32_t L, float* doc_y, dssm_stream_t stream) {
+    DSSM_REQUIRE(doc_positive_y && doc_negative_y && doc_y, DSSM_ERR_BAD_ARG, "dssm_merge_negative_doc: null pointer");
+    DSSM_REQUIRE(B > 0 && NEG >= 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_merge_negative_doc: bad shape");
+    const size_t total = (size_t)(1 + NEG) * B * L;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    merge_negative_doc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(doc_positive_y, doc_negative_y, B, NEG, L, doc_y);
+    LAUNCH_CHECK("merge_negative_doc");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_merge_negative_doc_index(int32_t B, int32_t NEG, int32_t* src, dssm_stream_t stream) {
+    DSSM_REQUIRE(src, DSSM_ERR_BAD_ARG, "dssm_merge_negative_doc_index: null pointer");
+    DSSM_REQUIRE(B > 0 && NEG >= 0, DSSM_ERR_BAD_SHAPE, "dssm_merge_negative_doc_index: bad shape");
+    merge_negative_doc_index_kernel<<<cdiv((int64_t)(1 + NEG) * B, 256), 256, 0, (cudaStream_t)stream>>>(B, NEG, src);
+    LAUNCH_CHECK("merge_negative_doc_index");
+    return DSSM_OK;
+}

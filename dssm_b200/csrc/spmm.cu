@@ -1,0 +1,461 @@
+// FC1: CSR bag-of-grams x W1 gather-accumulate (forward) and dW1 = X^T dH (backward).
+// Replaces tf.sparse_tensor_dense_matmul and its adjoint gradient, new_dssm.py:124-126.
+//
+// HBM-bound integer/gather work: one warp owns one output row, lanes cover the L1 columns with
+// 128-bit loads (L1=300 -> 75 float4, three per lane), column indices/values are loaded coalesced by
+// the warp and broadcast with shuffles, and GATHER_UNROLL independent W1-row loads are in flight per
+// lane before the first FMA.  Algorithmic bytes: nnz*(4*L1+8) + R*4*L1 + (R+1)*4.
+#include "common.cuh"
+
+namespace dssm {
+
+constexpr int GATHER_UNROLL = 4;
+constexpr int SPMM_THREADS = 256;
+constexpr int CSC_CHUNK = 128;  // entries of one column handled by one warp in the dW1 gather
+
+// acc[k] += sum_{p in [s,e)} val[p] * src4[idx[p]*L4 + lane + 32k]   (sequential in p)
+template <int NCH>
+__device__ __forceinline__ void gather_accumulate(const int* __restrict__ idx, const float* __restrict__ val, int s,
+                                                  int e, const float4* __restrict__ src4, int L4, int lane,
+                                                  float4 (&acc)[NCH]) {
+    for (int base = s; base < e; base += 32) {
+        const int n = min(32, e - base);
+        int my_c = 0;
+        float my_v = 0.f;
+        if (lane < n) {
+            my_c = __ldg(idx + base + lane);
+            my_v = __ldg(val + base + lane);
+        }
+        for (int t = 0; t < n; t += GATHER_UNROLL) {
+            float4 w[GATHER_UNROLL][NCH];
+            float vv[GATHER_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; ++u) {
+                const int tt = t + u;
+                const int c = __shfl_sync(0xffffffffu, my_c, tt & 31);
+                vv[u] = __shfl_sync(0xffffffffu, my_v, tt & 31);
+                const float4* rowp = src4 + (size_t)c * L4;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int col = lane + 32 * k;
+                    if (tt < n && col < L4)
+                        w[u][k] = __ldg(rowp + col);
+                    else
+                        w[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (tt >= n) vv[u] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; ++u) {
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    acc[k].x = fmaf(vv[u], w[u][k].x, acc[k].x);
+                    acc[k].y = fmaf(vv[u], w[u][k].y, acc[k].y);
+                    acc[k].z = fmaf(vv[u], w[u][k].z, acc[k].z);
+                    acc[k].w = fmaf(vv[u], w[u][k].w, acc[k].w);
+                }
+            }
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_fwd_v4_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ values,
+                   const float4* __restrict__ W4, const float4* __restrict__ bias4, float4* __restrict__ Y4, int R,
+                   int L4) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += stride) {
+        const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        float4 acc[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gather_accumulate<NCH>(indices, values, s, e, W4, L4, lane, acc);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            if (col < L4) {
+                float4 o = acc[k];
+                if (bias4) {
+                    const float4 b = __ldg(bias4 + col);
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                Y4[(size_t)row * L4 + col] = o;
+            }
+        }
+    }
+}
+
+// any L1 (not a multiple of 4, or wider than the vector kernels cover)
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_fwd_scalar_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                       const float* __restrict__ values, const float* __restrict__ W, const float* __restrict__ bias,
+                       float* __restrict__ Y, int R, int L1) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += stride) {
+        const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        for (int col = lane; col < L1; col += 32) {
+            float acc = 0.f;
+            for (int p = s; p < e; ++p)
+                acc = fmaf(__ldg(values + p), __ldg(W + (size_t)__ldg(indices + p) * L1 + col), acc);
+            Y[(size_t)row * L1 + col] = acc + (bias ? __ldg(bias + col) : 0.f);
+        }
+    }
+}
+
+template <int NCH>
+static void launch_fwd_v4(const int* indptr, const int* indices, const float* values, const float* W, const float* b,
+                          float* Y, int R, int L1, cudaStream_t st) {
+    const int wpb = SPMM_THREADS / 32;
+    int blocks = cdiv(R, wpb);
+    const int cap = sm_count() * 32;  // grid-stride beyond this
+    if (blocks > cap) blocks = cap;
+    spmm_fwd_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, (const float4*)W,
+                                                             (const float4*)b, (float4*)Y, R, L1 / 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, method 1: zero-fill + vector red scatter (cross-check path)
+template <int NCH>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_bwd_scatter_v4_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                           const float* __restrict__ values, const float4* __restrict__ dH4, float* __restrict__ dW,
+                           int R, int L4) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += stride) {
+        const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        float4 g[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            g[k] = col < L4 ? __ldg(dH4 + (size_t)row * L4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int p = s; p < e; ++p) {
+            const int c = __ldg(indices + p);
+            const float v = __ldg(values + p);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int col = lane + 32 * k;
+                if (col < L4)
+                    red_add4(dW + ((size_t)c * L4 + col) * 4, make_float4(v * g[k].x, v * g[k].y, v * g[k].z, v * g[k].w));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_bwd_scatter_scalar_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                               const float* __restrict__ values, const float* __restrict__ dH, float* __restrict__ dW,
+                               int R, int L1) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += stride) {
+        const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        for (int p = s; p < e; ++p) {
+            const int c = __ldg(indices + p);
+            const float v = __ldg(values + p);
+            for (int col = lane; col < L1; col += 32)
+                atomicAdd(dW + (size_t)c * L1 + col, v * __ldg(dH + (size_t)row * L1 + col));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, method 0: per-batch CSC (device-built) + gather-by-column.
+//
+//  csc_hist     colcnt[c] += 1 for every non-zero                       (int atomics, exact)
+//  csc_scan     colptr = exclusive_scan(colcnt); itemptr = exclusive_scan(max(1, ceil(cnt/CSC_CHUNK)))
+//  csc_fill     (row, value) of every non-zero into its column segment  (slot by atomic cursor)
+//  dw_gather    one warp per item (<= CSC_CHUNK entries of one column): sum value * dH[row,:];
+//               single-item columns write their dW1 row directly; multi-item columns park partial sums
+//               and the last-arriving item adds them in item order.
+// The slot order inside a column is whatever the atomics gave, so the fp32 summation order of a column
+// can differ between runs (last-bit differences); counts, columns and the set of terms are exact.
+
+__global__ void csc_hist_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int R,
+                                int* __restrict__ colcnt) {
+    const int nnz = __ldg(indptr + R);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
+        atomicAdd(colcnt + __ldg(indices + p), 1);
+}
+
+// single block; every thread scans a contiguous slice, block-level scan of the slice totals in smem
+__global__ void __launch_bounds__(1024)
+csc_scan_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ colptr, int* __restrict__ cursor,
+                int* __restrict__ itemptr) {
+    __shared__ int s_cnt[1024];
+    __shared__ int s_itm[1024];
+    const int t = threadIdx.x;
+    const int per = (D + blockDim.x - 1) / blockDim.x;
+    const int lo = min(D, t * per), hi = min(D, lo + per);
+    int a = 0, b = 0;
+    for (int c = lo; c < hi; ++c) {
+        const int n = colcnt[c];
+        a += n;
+        b += max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK);
+    }
+    s_cnt[t] = a;
+    s_itm[t] = b;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over blockDim.x totals
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+        int xa = 0, xb = 0;
+        if (t >= off) { xa = s_cnt[t - off]; xb = s_itm[t - off]; }
+        __syncthreads();
+        if (t >= off) { s_cnt[t] += xa; s_itm[t] += xb; }
+        __syncthreads();
+    }
+    int ra = s_cnt[t] - a, rb = s_itm[t] - b;  // exclusive prefix of this slice
+    for (int c = lo; c < hi; ++c) {
+        const int n = colcnt[c];
+        colptr[c] = ra;
+        cursor[c] = ra;
+        itemptr[c] = rb;
+        ra += n;
+        rb += max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK);
+    }
+    if (t == blockDim.x - 1) {
+        colptr[D] = s_cnt[t];
+        itemptr[D] = s_itm[t];
+    }
+}
+
+__global__ void __launch_bounds__(SPMM_THREADS)
+csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ values,
+                int R, int* __restrict__ cursor, int* __restrict__ csc_row, float* __restrict__ csc_val) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += stride) {
+        const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        for (int p = s + lane; p < e; p += 32) {
+            const int slot = atomicAdd(cursor + __ldg(indices + p), 1);
+            csc_row[slot] = row;
+            csc_val[slot] = __ldg(values + p);
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPMM_THREADS)
+dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ csc_row,
+                    const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
+                    float4* __restrict__ partial4, int* __restrict__ done, int D, int L4) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    const int n_items = __ldg(itemptr + D);
+    for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += stride) {
+        // column of this item: last c with itemptr[c] <= item
+        int lo = 0, hi = D;  // invariant: itemptr[lo] <= item < itemptr[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(itemptr + mid) <= item) lo = mid; else hi = mid;
+        }
+        const int c = lo;
+        const int first_item = __ldg(itemptr + c);
+        const int n_col_items = __ldg(itemptr + c + 1) - first_item;
+        const int cs = __ldg(colptr + c), ce = __ldg(colptr + c + 1);
+        const int s = cs + (item - first_item) * CSC_CHUNK;
+        const int e = min(ce, s + CSC_CHUNK);
+        float4 acc[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < e) gather_accumulate<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, acc);
+        if (n_col_items == 1) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int col = lane + 32 * k;
+                if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int col = lane + 32 * k;
+                if (col < L4) partial4[(size_t)item * L4 + col] = acc[k];
+            }
+            __threadfence();
+            __syncwarp();
+            int prev = 0;
+            if (lane == 0) prev = atomicAdd(done + c, 1);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == n_col_items - 1) {  // last item of the column: fold the partials in item order
+                __threadfence();
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < n_col_items; ++i) {
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        const int col = lane + 32 * k;
+                        if (col < L4) {
+                            const float4 p = __ldcg(partial4 + (size_t)(first_item + i) * L4 + col);
+                            acc[k].x += p.x; acc[k].y += p.y; acc[k].z += p.z; acc[k].w += p.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int col = lane + 32 * k;
+                    if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+                }
+                if (lane == 0) done[c] = 0;  // leave the counters clean for the next step
+            }
+        }
+    }
+}
+
+struct CscWorkspace {
+    int *colcnt, *done, *colptr, *cursor, *itemptr, *csc_row;
+    float* csc_val;
+    float* partial;
+    size_t bytes;
+};
+
+static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
+    Arena a(ws, (size_t)-1);
+    CscWorkspace w;
+    w.colcnt = a.take<int>(D + 1);   // colcnt and done are contiguous: one memset clears both
+    w.done = a.take<int>(D + 1);
+    w.colptr = a.take<int>(D + 1);
+    w.cursor = a.take<int>(D + 1);
+    w.itemptr = a.take<int>(D + 1);
+    w.csc_row = a.take<int>((size_t)max_nnz);
+    w.csc_val = a.take<float>((size_t)max_nnz);
+    const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
+    w.partial = a.take<float>(max_items * (size_t)L1);
+    w.bytes = a.off;
+    return w;
+}
+
+template <int NCH>
+static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, cudaStream_t st) {
+    const int blocks = sm_count() * 8;
+    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(w.colptr, w.itemptr, w.csc_row, w.csc_val,
+                                                            (const float4*)dH, (float4*)dW, (float4*)w.partial,
+                                                            w.done, D, L1 / 4);
+}
+
+template <int NCH>
+static void launch_scatter(const int* indptr, const int* indices, const float* values, const float* dH, float* dW,
+                           int R, int L1, cudaStream_t st) {
+    const int wpb = SPMM_THREADS / 32;
+    int blocks = cdiv(R, wpb);
+    const int cap = sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    spmm_bwd_scatter_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, (const float4*)dH, dW,
+                                                                   R, L1 / 4);
+}
+
+#define DISPATCH_NCH(nch, CALL)                       \
+    switch (nch) {                                    \
+        case 1: { constexpr int N_ = 1; CALL; } break; \
+        case 2: { constexpr int N_ = 2; CALL; } break; \
+        case 3: { constexpr int N_ = 3; CALL; } break; \
+        case 4: { constexpr int N_ = 4; CALL; } break; \
+        case 5: { constexpr int N_ = 5; CALL; } break; \
+        case 6: { constexpr int N_ = 6; CALL; } break; \
+        case 7: { constexpr int N_ = 7; CALL; } break; \
+        default: { constexpr int N_ = 8; CALL; } break; \
+    }
+
+}  // namespace dssm
+
+using namespace dssm;
+
+extern "C" int dssm_spmm_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
+                             const float* W1, const float* b1, int32_t L1, float* Y, dssm_stream_t stream) {
+    DSSM_REQUIRE(indptr && W1 && Y, DSSM_ERR_BAD_ARG, "dssm_spmm_fwd: null pointer");
+    DSSM_REQUIRE(R >= 0 && D > 0 && L1 > 0, DSSM_ERR_BAD_ARG, "dssm_spmm_fwd: bad sizes R=%d D=%d L1=%d", R, D, L1);
+    if (R == 0) return DSSM_OK;
+    DSSM_REQUIRE(indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_fwd: null indices/values");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (L1 % 4 == 0) && L1 <= 1024;
+    if (vec) {
+        DSSM_REQUIRE(aligned16(W1) && aligned16(Y) && (!b1 || aligned16(b1)), DSSM_ERR_BAD_ALIGN,
+                     "dssm_spmm_fwd: W1/b1/Y must be 16-byte aligned when L1 %% 4 == 0");
+        const int nch = cdiv(L1 / 4, 32);
+        DISPATCH_NCH(nch, launch_fwd_v4<N_>(indptr, indices, values, W1, b1, Y, R, L1, st));
+    } else {
+        const int wpb = SPMM_THREADS / 32;
+        int blocks = cdiv(R, wpb);
+        const int cap = sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        spmm_fwd_scalar_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, W1, b1, Y, R, L1);
+    }
+    LAUNCH_CHECK("spmm_fwd");
+    return DSSM_OK;
+}
+
+extern "C" size_t dssm_spmm_bwd_dw_workspace_bytes(int32_t R, int32_t D, int32_t L1, int64_t max_nnz) {
+    (void)R;
+    if (D <= 0 || L1 <= 0 || max_nnz < 0) return 0;
+    return carve_csc(nullptr, D, L1, max_nnz).bytes;
+}
+
+extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R,
+                                int32_t D, const float* dH, int32_t L1, float* dW1, int32_t method, void* workspace,
+                                size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(indptr && dH && dW1, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: null pointer");
+    DSSM_REQUIRE(R >= 0 && D > 0 && L1 > 0, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: bad sizes");
+    DSSM_REQUIRE(method == 0 || method == 1, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: unknown method %d", method);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (L1 % 4 == 0) && L1 <= 1024;
+    if (vec)
+        DSSM_REQUIRE(aligned16(dH) && aligned16(dW1), DSSM_ERR_BAD_ALIGN, "dssm_spmm_bwd_dw: dH/dW1 must be 16-byte aligned");
+    if (method == 1 || !vec || R == 0) {
+        CUDA_TRY(cudaMemsetAsync(dW1, 0, (size_t)D * L1 * sizeof(float), st));
+        if (R == 0) return DSSM_OK;
+        DSSM_REQUIRE(indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: null indices/values");
+        if (vec) {
+            const int nch = cdiv(L1 / 4, 32);
+            DISPATCH_NCH(nch, launch_scatter<N_>(indptr, indices, values, dH, dW1, R, L1, st));
+        } else {
+            const int wpb = SPMM_THREADS / 32;
+            int blocks = cdiv(R, wpb);
+            const int cap = sm_count() * 32;
+            if (blocks > cap) blocks = cap;
+            spmm_bwd_scatter_scalar_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, dH, dW1, R, L1);
+        }
+        LAUNCH_CHECK("spmm_bwd_scatter");
+        return DSSM_OK;
+    }
+    DSSM_REQUIRE(indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: null indices/values");
+    DSSM_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, DSSM_ERR_BAD_ALIGN,
+                 "dssm_spmm_bwd_dw: workspace must be 256-byte aligned");
+    // capacity check: the caller sized the workspace for max_nnz; recover it from the byte count
+    const size_t fixed = carve_csc(nullptr, D, L1, 0).bytes;
+    DSSM_REQUIRE(workspace_bytes >= fixed, DSSM_ERR_WORKSPACE, "dssm_spmm_bwd_dw: workspace %zu < %zu", workspace_bytes, fixed);
+    // largest max_nnz whose carve fits (monotone): binary search on the host, cheap
+    int64_t lo = 0, hi = (int64_t)1 << 40;
+    while (hi - lo > 1) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (carve_csc(nullptr, D, L1, mid).bytes <= workspace_bytes) lo = mid; else hi = mid;
+    }
+    const int64_t cap_nnz = lo;
+    CscWorkspace w = carve_csc(workspace, D, L1, cap_nnz);
+    // NOTE: nnz lives on the device (indptr[R]); the caller guarantees nnz <= the max_nnz it sized for.
+    CUDA_TRY(cudaMemsetAsync(w.colcnt, 0, (size_t)((char*)w.colptr - (char*)w.colcnt), st));
+    const int nsm = sm_count();
+    csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
+    LAUNCH_CHECK("csc_hist");
+    csc_scan_kernel<<<1, 1024, 0, st>>>(w.colcnt, D, w.colptr, w.cursor, w.itemptr);
+    LAUNCH_CHECK("csc_scan");
+    {
+        const int wpb = SPMM_THREADS / 32;
+        int blocks = cdiv(R, wpb);
+        if (blocks > nsm * 32) blocks = nsm * 32;
+        csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.csc_row, w.csc_val);
+        LAUNCH_CHECK("csc_fill");
+    }
+    const int nch = cdiv(L1 / 4, 32);
+    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, st));
+    LAUNCH_CHECK("dw_gather");
+    return DSSM_OK;
+}

@@ -1,0 +1,428 @@
+// Tower handle: the graph of new_dssm.py:104-217 (input -> FC1 -> BN1 -> FC2 -> BN2 -> Merge_Negative_Doc ->
+// Cosine_Similarity -> Loss -> Training) as one sequence of kernel launches over caller-owned buffers.
+// One C call per sess.run(train_step): no Python between the kernels, and the whole step can be captured
+// into a CUDA graph because every launch geometry depends only on (B, NEG, D, layers), never on nnz.
+#include "common.cuh"
+#include <string>
+#include <vector>
+#include <string.h>
+
+namespace dssm {
+
+struct TensorInfo {
+    std::string name;
+    int64_t off;  // floats; for kind 2 relative to the workspace base
+    int64_t rows, cols;
+};
+
+static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
+
+}  // namespace dssm
+
+using namespace dssm;
+
+struct dssm_tower {
+    dssm_config cfg;
+    int n_layers, R, B, NEG, D;
+    int L[DSSM_MAX_LAYERS + 1];  // L[0] = D, L[l] = width of layer l
+    std::vector<TensorInfo> params, ema, wst;
+    int64_t P, E;
+    // bound buffers
+    float *params_p, *grads_p, *m_p, *v_p, *ema_p, *beta_pow_p;
+    char* ws;
+    size_t ws_bytes;
+    int64_t max_nnz;
+    bool bound, fwd_train_done;
+    // workspace carve (device pointers)
+    int32_t *st_indptr, *st_indices;
+    float* st_values;
+    float* h[DSSM_MAX_LAYERS + 1];
+    float* dh[DSSM_MAX_LAYERS + 1];
+    float *bn_mean[DSSM_MAX_LAYERS + 1], *bn_var[DSSM_MAX_LAYERS + 1], *bn_rstd[DSSM_MAX_LAYERS + 1],
+        *bn_scale[DSSM_MAX_LAYERS + 1], *bn_shift[DSSM_MAX_LAYERS + 1];
+    float *Y, *qnorm, *dnorm, *cos_raw, *cos_sim, *prob, *loss_terms, *loss;
+    void *bn_ws, *dw_ws, *sp_ws;
+    size_t bn_ws_bytes, dw_ws_bytes, sp_ws_bytes;
+    // last forward's CSR (backward reuses it)
+    const int32_t *cur_indptr, *cur_indices;
+    const float* cur_values;
+    // graph
+    cudaGraph_t graph;
+    cudaGraphExec_t graph_exec;
+    int64_t launches_per_step;
+    int64_t launches;
+
+    int find(const std::vector<TensorInfo>& v, const std::string& n) const {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].name == n) return (int)i;
+        return -1;
+    }
+    float* P_(const std::string& n) const { return params_p + params[find(params, n)].off; }
+    float* G_(const std::string& n) const { return grads_p + params[find(params, n)].off; }
+    float* E_(const std::string& n) const { return ema_p + ema[find(ema, n)].off; }
+};
+
+static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
+    Arena a(base, (size_t)-1);
+    const int R = t->R, B = t->B, NEG = t->NEG, n = t->n_layers;
+    t->wst.clear();
+    auto reg = [&](const std::string& name, float* p, int64_t rows, int64_t cols) {
+        t->wst.push_back({name, (int64_t)(((char*)p - base) / (int64_t)sizeof(float)), rows, cols});
+    };
+    t->st_indptr = a.take<int32_t>(R + 1);
+    t->st_indices = a.take<int32_t>((size_t)max_nnz);
+    t->st_values = a.take<float>((size_t)max_nnz);
+    for (int l = 1; l <= n; ++l) {
+        t->h[l] = a.take<float>((size_t)R * t->L[l]);
+        reg("h" + std::to_string(l), t->h[l], R, t->L[l]);
+    }
+    for (int l = 1; l <= n; ++l) {
+        t->dh[l] = a.take<float>((size_t)R * t->L[l]);
+        reg("dh" + std::to_string(l), t->dh[l], R, t->L[l]);
+    }
+    if (t->cfg.use_bn) {
+        for (int l = 1; l <= n; ++l) {
+            const std::string pre = "bn" + std::to_string(l) + "_";
+            float** arrs[5] = {&t->bn_mean[l], &t->bn_var[l], &t->bn_rstd[l], &t->bn_scale[l], &t->bn_shift[l]};
+            const char* nm[5] = {"mean", "var", "rstd", "scale", "shift"};
+            for (int i = 0; i < 5; ++i) {
+                *arrs[i] = a.take<float>((size_t)2 * t->L[l]);
+                reg(pre + nm[i], *arrs[i], 2, t->L[l]);
+            }
+        }
+    }
+    const int Ll = t->L[n];
+    t->Y = a.take<float>((size_t)R * Ll);
+    reg("Y", t->Y, R, Ll);
+    t->qnorm = a.take<float>(B);
+    reg("query_norm_single", t->qnorm, B, 1);
+    t->dnorm = a.take<float>((size_t)(1 + NEG) * B);
+    reg("doc_norm", t->dnorm, (int64_t)(1 + NEG) * B, 1);
+    t->cos_raw = a.take<float>((size_t)(1 + NEG) * B);
+    reg("cos_sim_raw", t->cos_raw, (int64_t)(1 + NEG) * B, 1);
+    t->cos_sim = a.take<float>((size_t)(1 + NEG) * B);
+    reg("cos_sim", t->cos_sim, B, 1 + NEG);
+    t->prob = a.take<float>((size_t)(1 + NEG) * B);
+    reg("prob", t->prob, B, 1 + NEG);
+    t->loss_terms = a.take<float>(B);
+    reg("loss_terms", t->loss_terms, B, 1);
+    t->loss = a.take<float>(4);
+    reg("loss", t->loss, 1, 1);
+    // scratch
+    int maxL = 0;
+    for (int l = 1; l <= n; ++l) maxL = t->L[l] > maxL ? t->L[l] : maxL;
+    t->bn_ws_bytes = dssm_bn_workspace_bytes(R, maxL);
+    t->bn_ws = a.take<char>(t->bn_ws_bytes);
+    size_t dw = dssm_colsum_workspace_bytes(R, maxL);
+    for (int l = 2; l <= n; ++l) {
+        const size_t x = dssm_fc_bwd_dw_workspace_bytes(R, t->L[l - 1], t->L[l]);
+        dw = x > dw ? x : dw;
+    }
+    t->dw_ws_bytes = dw;
+    t->dw_ws = a.take<char>(dw);
+    t->sp_ws_bytes = dssm_spmm_bwd_dw_workspace_bytes(R, t->D, t->L[1], max_nnz);
+    t->sp_ws = a.take<char>(t->sp_ws_bytes);
+    return a.off;
+}
+
+extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
+    DSSM_REQUIRE(cfg && out, DSSM_ERR_BAD_ARG, "dssm_tower_create: null pointer");
+    DSSM_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= DSSM_MAX_LAYERS, DSSM_ERR_BAD_ARG, "dssm_tower_create: n_layers=%d out of [1,%d]", cfg->n_layers, DSSM_MAX_LAYERS);
+    DSSM_REQUIRE(cfg->TRIGRAM_D > 0 && cfg->NEG > 0 && cfg->query_BS > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: TRIGRAM_D, NEG, query_BS must be positive");
+    DSSM_REQUIRE(cfg->act == DSSM_ACT_RELU || cfg->act == DSSM_ACT_TANH || cfg->act == DSSM_ACT_NONE, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown act %d", cfg->act);
+    DSSM_REQUIRE(cfg->gemm_mode == DSSM_GEMM_FP32 || cfg->gemm_mode == DSSM_GEMM_BF16_TC, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown gemm_mode %d", cfg->gemm_mode);
+    for (int l = 0; l < cfg->n_layers; ++l)
+        DSSM_REQUIRE(cfg->layers[l] > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: layer %d width %d", l + 1, cfg->layers[l]);
+    const int64_t rows = (int64_t)(2 + cfg->NEG) * cfg->query_BS;
+    DSSM_REQUIRE(rows < (int64_t)1 << 30, DSSM_ERR_BAD_SHAPE, "dssm_tower_create: (2+NEG)*query_BS too large");
+    dssm_tower* t = new dssm_tower();
+    t->cfg = *cfg;
+    t->n_layers = cfg->n_layers;
+    t->B = cfg->query_BS;
+    t->NEG = cfg->NEG;
+    t->D = cfg->TRIGRAM_D;
+    t->R = (int)rows;
+    t->L[0] = t->D;
+    for (int l = 1; l <= t->n_layers; ++l) t->L[l] = cfg->layers[l - 1];
+    int64_t off = 0;
+    for (int l = 1; l <= t->n_layers; ++l) {
+        t->params.push_back({"W" + std::to_string(l), off, t->L[l - 1], t->L[l]});
+        off += pad4((int64_t)t->L[l - 1] * t->L[l]);
+        t->params.push_back({"b" + std::to_string(l), off, 1, t->L[l]});
+        off += pad4(t->L[l]);
+    }
+    int64_t eoff = 0;
+    if (cfg->use_bn) {
+        for (int l = 1; l <= t->n_layers; ++l) {
+            t->params.push_back({"bn" + std::to_string(l) + "_gamma", off, 2, t->L[l]});
+            off += pad4(2 * (int64_t)t->L[l]);
+            t->params.push_back({"bn" + std::to_string(l) + "_beta", off, 2, t->L[l]});
+            off += pad4(2 * (int64_t)t->L[l]);
+            t->ema.push_back({"bn" + std::to_string(l) + "_ema_mean", eoff, 2, t->L[l]});
+            eoff += pad4(2 * (int64_t)t->L[l]);
+            t->ema.push_back({"bn" + std::to_string(l) + "_ema_var", eoff, 2, t->L[l]});
+            eoff += pad4(2 * (int64_t)t->L[l]);
+        }
+    }
+    t->P = off;
+    t->E = eoff;
+    t->bound = false;
+    t->fwd_train_done = false;
+    t->graph = nullptr;
+    t->graph_exec = nullptr;
+    t->launches_per_step = 0;
+    t->launches = 0;
+    tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
+    *out = t;
+    return DSSM_OK;
+}
+
+extern "C" void dssm_tower_destroy(dssm_tower* t) {
+    if (!t) return;
+    if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+    if (t->graph) cudaGraphDestroy(t->graph);
+    delete t;
+}
+
+extern "C" int64_t dssm_tower_param_count(const dssm_tower* t) { return t ? t->P : -1; }
+extern "C" int64_t dssm_tower_ema_count(const dssm_tower* t) { return t ? t->E : -1; }
+
+extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nnz) {
+    if (!t || max_nnz < 0) return 0;
+    dssm_tower tmp = *t;
+    tmp.graph = nullptr;
+    tmp.graph_exec = nullptr;
+    return tower_carve(&tmp, nullptr, max_nnz);
+}
+
+extern "C" int32_t dssm_tower_num_tensors(const dssm_tower* t, int32_t kind) {
+    if (!t) return -1;
+    if (kind == 0) return (int32_t)t->params.size();
+    if (kind == 1) return (int32_t)t->ema.size();
+    if (kind == 2) return (int32_t)t->wst.size();
+    return -1;
+}
+
+extern "C" int dssm_tower_tensor_info(const dssm_tower* t, int32_t kind, int32_t index, char* name, int32_t name_cap,
+                                      int64_t* offset_floats, int64_t* rows, int64_t* cols) {
+    DSSM_REQUIRE(t, DSSM_ERR_BAD_ARG, "dssm_tower_tensor_info: null tower");
+    const std::vector<TensorInfo>* v = kind == 0 ? &t->params : kind == 1 ? &t->ema : kind == 2 ? &t->wst : nullptr;
+    DSSM_REQUIRE(v && index >= 0 && index < (int)v->size(), DSSM_ERR_BAD_ARG, "dssm_tower_tensor_info: bad kind/index %d/%d", kind, index);
+    const TensorInfo& ti = (*v)[index];
+    if (name && name_cap > 0) {
+        strncpy(name, ti.name.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (offset_floats) *offset_floats = ti.off;
+    if (rows) *rows = ti.rows;
+    if (cols) *cols = ti.cols;
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float* m, float* v, float* ema,
+                               float* beta_pow, void* workspace, size_t workspace_bytes, int64_t max_nnz) {
+    DSSM_REQUIRE(t && params && workspace, DSSM_ERR_BAD_ARG, "dssm_tower_bind: null pointer");
+    DSSM_REQUIRE(!t->cfg.use_bn || ema, DSSM_ERR_BAD_ARG, "dssm_tower_bind: ema buffer required with use_bn");
+    DSSM_REQUIRE(aligned16(params) && (!grads || aligned16(grads)) && (!m || aligned16(m)) && (!v || aligned16(v)) && (!ema || aligned16(ema)),
+                 DSSM_ERR_BAD_ALIGN, "dssm_tower_bind: buffers must be 16-byte aligned");
+    DSSM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, DSSM_ERR_BAD_ALIGN, "dssm_tower_bind: workspace must be 256-byte aligned");
+    DSSM_REQUIRE(max_nnz > 0 && max_nnz < (int64_t)1 << 31, DSSM_ERR_BAD_ARG, "dssm_tower_bind: max_nnz out of range");
+    const size_t need = dssm_tower_workspace_bytes(t, max_nnz);
+    DSSM_REQUIRE(workspace_bytes >= need, DSSM_ERR_WORKSPACE, "dssm_tower_bind: workspace %zu < required %zu", workspace_bytes, need);
+    if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+    if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+    t->params_p = params; t->grads_p = grads; t->m_p = m; t->v_p = v; t->ema_p = ema; t->beta_pow_p = beta_pow;
+    t->ws = (char*)workspace;
+    t->ws_bytes = workspace_bytes;
+    t->max_nnz = max_nnz;
+    tower_carve(t, t->ws, max_nnz);
+    t->bound = true;
+    t->fwd_train_done = false;
+    return DSSM_OK;
+}
+
+#define TRY(call)                  \
+    do {                           \
+        int _rc = (call);          \
+        if (_rc != DSSM_OK) return _rc; \
+    } while (0)
+
+static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                              int on_train, int update_ema, bool want_grad, dssm_stream_t s) {
+    const dssm_config& c = t->cfg;
+    const int n = t->n_layers, R = t->R, B = t->B;
+    TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
+    for (int l = 1; l <= n; ++l) {
+        const std::string ls = std::to_string(l);
+        if (c.use_bn) {
+            TRY(dssm_bn_forward(t->h[l], R, t->L[l], B, on_train, update_ema, t->P_("bn" + ls + "_gamma"),
+                                t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
+                                c.bn_eps, c.ema_decay, t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l],
+                                t->bn_shift[l], t->bn_ws, t->bn_ws_bytes, s));
+        }
+        const float* sc = c.use_bn ? t->bn_scale[l] : nullptr;
+        const float* sh = c.use_bn ? t->bn_shift[l] : nullptr;
+        if (l < n) {
+            const std::string ns = std::to_string(l + 1);
+            TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
+                            t->h[l + 1], c.gemm_mode, s));
+        } else {
+            TRY(dssm_bn_act_apply(t->h[l], R, t->L[l], B, sc, sh, c.act, t->Y, s));
+        }
+    }
+    TRY(dssm_cos_softmax_loss(t->Y, B, t->NEG, t->L[n], c.gamma, c.loss_eps, c.loss_div_bs, t->qnorm, t->dnorm,
+                              t->cos_raw, t->cos_sim, t->prob, t->loss_terms, t->loss, want_grad ? t->dh[n] : nullptr, s));
+    t->cur_indptr = indptr; t->cur_indices = indices; t->cur_values = values;
+    t->fwd_train_done = want_grad && on_train;
+    return DSSM_OK;
+}
+
+static int tower_backward_impl(dssm_tower* t, dssm_stream_t s) {
+    const dssm_config& c = t->cfg;
+    const int n = t->n_layers, R = t->R, B = t->B;
+    for (int l = n; l >= 1; --l) {
+        const std::string ls = std::to_string(l);
+        if (c.use_bn) {
+            TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, t->P_("bn" + ls + "_gamma"), t->bn_mean[l],
+                                     t->bn_rstd[l], t->bn_scale[l], t->bn_shift[l], t->G_("bn" + ls + "_gamma"),
+                                     t->G_("bn" + ls + "_beta"), t->bn_ws, t->bn_ws_bytes, s));
+        } else {
+            TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                     nullptr, nullptr, nullptr, 0, s));
+        }
+        if (l > 1) {
+            const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
+            const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
+            TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
+                               t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
+            TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, s));
+        } else {
+            TRY(dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1], t->G_("W1"), 0,
+                                 t->sp_ws, t->sp_ws_bytes, s));
+            TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
+        }
+    }
+    return DSSM_OK;
+}
+
+static int tower_adam_impl(dssm_tower* t, float grad_scale, dssm_stream_t s) {
+    const dssm_config& c = t->cfg;
+    TRY(dssm_adam_step(t->params_p, t->grads_p, t->m_p, t->v_p, t->P, t->beta_pow_p, c.learning_rate, c.beta1, c.beta2,
+                       c.adam_eps, grad_scale, s));
+    TRY(dssm_adam_advance(t->beta_pow_p, c.beta1, c.beta2, s));
+    return DSSM_OK;
+}
+
+struct LaunchScope {
+    dssm_tower* t;
+    int64_t start;
+    explicit LaunchScope(dssm_tower* t_) : t(t_), start(g_launch_count) {}
+    ~LaunchScope() { t->launches += g_launch_count - start; }
+};
+
+extern "C" int dssm_tower_forward(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                                  int32_t on_train, int32_t update_ema, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_forward: tower not bound");
+    DSSM_REQUIRE(indptr && indices && values, DSSM_ERR_BAD_ARG, "dssm_tower_forward: null CSR pointer");
+    LaunchScope ls(t);
+    return tower_forward_impl(t, indptr, indices, values, on_train, update_ema, on_train != 0, stream);
+}
+
+extern "C" int dssm_tower_backward(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_backward: tower not bound");
+    DSSM_REQUIRE(t->grads_p, DSSM_ERR_STATE, "dssm_tower_backward: no grads buffer bound");
+    DSSM_REQUIRE(t->fwd_train_done, DSSM_ERR_STATE, "dssm_tower_backward: needs a preceding training-mode forward");
+    LaunchScope ls(t);
+    t->fwd_train_done = false;
+    return tower_backward_impl(t, stream);
+}
+
+extern "C" int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_adam: tower not bound");
+    DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_adam: optimizer buffers not bound");
+    LaunchScope ls(t);
+    return tower_adam_impl(t, grad_scale, stream);
+}
+
+static int tower_step_impl(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                           dssm_stream_t s) {
+    TRY(tower_forward_impl(t, indptr, indices, values, 1, 1, true, s));
+    TRY(tower_backward_impl(t, s));
+    t->fwd_train_done = false;
+    TRY(tower_adam_impl(t, 1.0f, s));
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_train_step(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                                     dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_train_step: tower not bound");
+    DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_train_step: optimizer buffers not bound");
+    DSSM_REQUIRE(indptr && indices && values, DSSM_ERR_BAD_ARG, "dssm_tower_train_step: null CSR pointer");
+    LaunchScope ls(t);
+    return tower_step_impl(t, indptr, indices, values, stream);
+}
+
+extern "C" int dssm_tower_staging(dssm_tower* t, int32_t** indptr, int32_t** indices, float** values) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_staging: tower not bound");
+    if (indptr) *indptr = t->st_indptr;
+    if (indices) *indices = t->st_indices;
+    if (values) *values = t->st_values;
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_capture_graph(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_capture_graph: tower not bound");
+    DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_capture_graph: optimizer buffers not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSSM_REQUIRE(st != nullptr, DSSM_ERR_BAD_ARG, "dssm_tower_capture_graph: needs a non-default stream");
+    if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+    if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+    const int64_t before = g_launch_count;
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != DSSM_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail(DSSM_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    t->launches_per_step = g_launch_count - before;
+    t->graph = g;
+    CUDA_TRY(cudaGraphInstantiate(&t->graph_exec, t->graph, 0));
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_train_step_staged: tower not bound");
+    if (t->graph_exec) {
+        CUDA_TRY(cudaGraphLaunch(t->graph_exec, (cudaStream_t)stream));
+        t->launches += t->launches_per_step;
+        return DSSM_OK;
+    }
+    return dssm_tower_train_step(t, t->st_indptr, t->st_indices, t->st_values, stream);
+}
+
+extern "C" int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                          const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_train_step_host: tower not bound");
+    DSSM_REQUIRE(host_indptr && host_indices && host_values, DSSM_ERR_BAD_ARG, "dssm_tower_train_step_host: null CSR pointer");
+    DSSM_REQUIRE(nnz >= 0 && nnz <= t->max_nnz, DSSM_ERR_WORKSPACE, "dssm_tower_train_step_host: nnz %lld exceeds bound max_nnz %lld",
+                 (long long)nnz, (long long)t->max_nnz);
+    DSSM_REQUIRE(host_indptr[0] == 0 && host_indptr[t->R] == nnz, DSSM_ERR_BAD_SHAPE,
+                 "dssm_tower_train_step_host: batch must have exactly (2+NEG)*query_BS = %d rows and indptr[R] == nnz", t->R);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(t->st_indptr, host_indptr, (size_t)(t->R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        CUDA_TRY(cudaMemcpyAsync(t->st_indices, host_indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(t->st_values, host_values, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    TRY(dssm_tower_train_step_staged(t, stream));
+    if (host_loss) {
+        CUDA_TRY(cudaMemcpyAsync(host_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return DSSM_OK;
+}
+
+extern "C" int64_t dssm_tower_launch_count(const dssm_tower* t) { return t ? t->launches : -1; }

@@ -1,0 +1,58 @@
+"""Corpus cosine top-k (north_star item 5; no reference function exists -- SURVEY.md section 8 row a13).
+
+Scores follow new_dssm.py:185-197 (dot / (||q||*||d||), no epsilon); ordering follows
+tf.nn.top_k(sorted=True) (utils/tf_ranking_utils.py:47): score descending, ties to the lower doc id.
+Document-sharded: every rank scores its contiguous id range, local top-k lists are all-gathered and merged.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def corpus_topk(Q: torch.Tensor, docs: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores [nq,k] fp32, ids [nq,k] int32), sorted; ids = id_offset + local row."""
+    if not (Q.is_cuda and docs.is_cuda):
+        raise ValueError("corpus_topk takes CUDA tensors (there is no CPU path)")
+    nq, d = Q.shape
+    nd = docs.shape[0]
+    k = min(k, nd)
+    nb = lib.dssm_corpus_topk_workspace_bytes(nq, nd, d, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=Q.device)
+    s = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+    i = torch.empty((nq, k), dtype=torch.int32, device=Q.device)
+    check(lib.dssm_corpus_topk(ptr(Q), nq, ptr(docs), nd, d, k, id_offset, ptr(s), ptr(i), ptr(ws), nb, stream_ptr()))
+    return s, i
+
+
+def topk_merge(part_scores: torch.Tensor, part_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """part_* [n_parts, nq, k] (each part sorted) -> global (scores, ids) [nq, k]."""
+    n_parts, nq, k = part_scores.shape
+    s = torch.empty((nq, k), dtype=torch.float32, device=part_scores.device)
+    i = torch.empty((nq, k), dtype=torch.int32, device=part_scores.device)
+    check(lib.dssm_topk_merge(ptr(part_scores.contiguous()), ptr(part_ids.contiguous()), n_parts, nq, k, ptr(s), ptr(i), stream_ptr()))
+    return s, i
+
+
+def shard_range(n_docs: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous id range [lo, hi) owned by `rank`."""
+    per = (n_docs + world - 1) // world
+    lo = min(n_docs, rank * per)
+    return lo, min(n_docs, lo + per)
+
+
+def sharded_corpus_topk(Q: torch.Tensor, local_docs: torch.Tensor, k: int, id_offset: int, group=None):
+    """Every rank: local top-k over its shard, NCCL all-gather of the (scores, ids) lists, merge on every rank."""
+    s, i = corpus_topk(Q, local_docs, k, id_offset)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return s, i
+    gs = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
+    gi = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+    dist.all_gather_into_tensor(gs, s, group=group)
+    dist.all_gather_into_tensor(gi, i, group=group)
+    return topk_merge(gs, gi)

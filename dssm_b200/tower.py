@@ -1,0 +1,299 @@
+"""DSSMTower: the reference graph (semantic_matching/dssm/new_dssm.py:104-217) as a drop-in tower.
+
+The reference drives its graph with ``sess.run(fetch, feed_dict=pull_batch(...))`` (new_dssm.py:261-286) and
+looks tensors up by graph name (load_model_and_save_vector.py:30-46).  ``DSSMTower.run`` keeps that call
+shape; ``train_step`` / ``forward`` are the direct forms.  All arithmetic happens in libdssm_b200.so -- one C
+call per step; torch owns the device memory and the stream, nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, GEMM, check, lib, ptr, stream_ptr
+from .batch import DOC_NEG_BATCH, DOC_POS_BATCH, ON_TRAIN, QUERY_BATCH, StackedBatch, stack_feed
+from .config import Config
+from .ops import DeviceCSR
+from .synthetic import init_params
+
+# reference graph names -> tower tensors (new_dssm.py:156-158,185-199,206-209; with ":0" or scope prefix accepted)
+_ALIASES = {
+    "embedding_query_y": "embedding_query_y",
+    "embedding_doc_positive_y": "embedding_doc_positive_y",
+    "embedding_doc_negative_y": "embedding_doc_negative_y",
+    "query_norm_single": "query_norm_single",
+    "doc_norm": "doc_norm",
+    "cos_sim_raw": "cos_sim_raw",
+    "cos_sim": "cos_sim",
+    "prob": "prob",
+    "hit_prob": "hit_prob",
+    "loss": "loss",
+    "accuracy": "accuracy",
+}
+
+
+def _make_c_config(conf: Config) -> _lib.dssm_config:
+    c = _lib.dssm_config()
+    c.TRIGRAM_D, c.n_layers = conf.TRIGRAM_D, len(conf.layers)
+    for i, n in enumerate(conf.layers):
+        c.layers[i] = n
+    c.NEG, c.query_BS = conf.NEG, conf.query_BS
+    c.use_bn, c.act = int(conf.use_bn), ACT[conf.act]
+    c.loss_div_bs, c.gemm_mode = int(conf.loss_div_bs), GEMM[conf.gemm_mode]
+    c.bn_eps, c.ema_decay, c.gamma, c.loss_eps = conf.bn_eps, conf.ema_decay, conf.gamma, conf.loss_eps
+    c.learning_rate, c.beta1, c.beta2, c.adam_eps = conf.learning_rate, conf.beta1, conf.beta2, conf.adam_eps
+    return c
+
+
+class DSSMTower:
+    def __init__(self, conf: Config, max_nnz: int, device: Union[str, torch.device] = "cuda",
+                 params: Optional[Dict[str, np.ndarray]] = None, seed: int = 0):
+        if len(conf.layers) > _lib.MAX_LAYERS:
+            raise ValueError("too many layers")
+        self.conf = conf
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DSSMTower needs a CUDA device (there is no CPU path)")
+        self.max_nnz = int(max_nnz)
+        self._h = C.c_void_p()
+        cc = _make_c_config(conf)
+        check(lib.dssm_tower_create(C.byref(cc), C.byref(self._h)))
+        self.P = lib.dssm_tower_param_count(self._h)
+        self.E = lib.dssm_tower_ema_count(self._h)
+        with torch.cuda.device(self.device):
+            z = lambda n: torch.zeros(max(int(n), 4), dtype=torch.float32, device=self.device)
+            self.params, self.grads, self.m, self.v, self.ema = z(self.P), z(self.P), z(self.P), z(self.P), z(self.E)
+            self.beta_pow = torch.tensor([conf.beta1, conf.beta2], dtype=torch.float32, device=self.device)
+            ws_bytes = lib.dssm_tower_workspace_bytes(self._h, self.max_nnz)
+            self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
+            check(lib.dssm_tower_bind(self._h, ptr(self.params), ptr(self.grads), ptr(self.m), ptr(self.v), ptr(self.ema),
+                                      ptr(self.beta_pow), ptr(self.workspace), ws_bytes, self.max_nnz))
+        self._layout = {k: self._tensor_table(k) for k in (0, 1, 2)}
+        self._ws_f32 = self.workspace.view(torch.float32)
+        self.load_params(params if params is not None else init_params(conf, seed))
+        self._graph = False
+        self._pinned = None
+        self._host_loss = torch.zeros(1, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib.dssm_tower_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- layout ---------------------------------------------------------------------------------------
+    def _tensor_table(self, kind: int):
+        out = {}
+        name = C.create_string_buffer(64)
+        off, rows, cols = C.c_int64(), C.c_int64(), C.c_int64()
+        for i in range(lib.dssm_tower_num_tensors(self._h, kind)):
+            check(lib.dssm_tower_tensor_info(self._h, kind, i, name, 64, C.byref(off), C.byref(rows), C.byref(cols)))
+            out[name.value.decode()] = (off.value, rows.value, cols.value)
+        return out
+
+    def _view(self, buf: torch.Tensor, entry):
+        off, rows, cols = entry
+        return buf[off:off + rows * cols].view(rows, cols)
+
+    def param(self, name: str, which: str = "params") -> torch.Tensor:
+        """View of a named tensor inside the flat params / grads / m / v buffer (names: W{l}, b{l},
+        bn{l}_gamma, bn{l}_beta with [2,L] = (query, doc) instances)."""
+        return self._view(getattr(self, which), self._layout[0][name])
+
+    def ema_tensor(self, name: str) -> torch.Tensor:
+        return self._view(self.ema, self._layout[1][name])
+
+    def tensor(self, name: str) -> torch.Tensor:
+        """A tensor of the last forward/backward by graph name (reference names accepted, e.g.
+        'BN2/embedding_query_y:0')."""
+        key = name.split("/")[-1].split(":")[0]
+        B = self.conf.query_BS
+        if key in self._layout[2]:
+            return self._view(self._ws_f32, self._layout[2][key])
+        if key == "embedding_query_y":
+            return self.tensor("Y")[:B]
+        if key == "embedding_doc_positive_y":
+            return self.tensor("Y")[B:2 * B]
+        if key == "embedding_doc_negative_y":
+            return self.tensor("Y")[2 * B:]
+        if key == "hit_prob":
+            return self.tensor("prob")[:, 0:1]
+        if key == "accuracy":  # new_dssm.py:220-221
+            return (torch.argmax(self.tensor("prob"), dim=1) == 0).float().mean()
+        if key in self._layout[0]:
+            return self.param(key)
+        if key in self._layout[1]:
+            return self.ema_tensor(key)
+        raise KeyError(name)
+
+    # ---- parameters -----------------------------------------------------------------------------------
+    def load_params(self, p: Dict[str, np.ndarray]) -> None:
+        """Accepts the oracle/synthetic naming: W{l}, b{l}, bn{l}_{q|d}_{beta|gamma}."""
+        n = len(self.conf.layers)
+        for l in range(1, n + 1):
+            self.param(f"W{l}").copy_(torch.from_numpy(np.ascontiguousarray(p[f"W{l}"], dtype=np.float32)))
+            self.param(f"b{l}").copy_(torch.from_numpy(np.ascontiguousarray(p[f"b{l}"], dtype=np.float32)).view(1, -1))
+            if self.conf.use_bn:
+                for which in ("gamma", "beta"):
+                    stacked = np.stack([p[f"bn{l}_q_{which}"], p[f"bn{l}_d_{which}"]]).astype(np.float32)
+                    self.param(f"bn{l}_{which}").copy_(torch.from_numpy(stacked))
+
+    def _export(self, which: str) -> Dict[str, np.ndarray]:
+        out = {}
+        n = len(self.conf.layers)
+        for l in range(1, n + 1):
+            out[f"W{l}"] = self.param(f"W{l}", which).cpu().numpy().copy()
+            out[f"b{l}"] = self.param(f"b{l}", which).cpu().numpy().reshape(-1).copy()
+            if self.conf.use_bn:
+                for w in ("gamma", "beta"):
+                    t = self.param(f"bn{l}_{w}", which).cpu().numpy()
+                    out[f"bn{l}_q_{w}"], out[f"bn{l}_d_{w}"] = t[0].copy(), t[1].copy()
+        return out
+
+    def export_params(self):
+        return self._export("params")
+
+    def export_grads(self):
+        return self._export("grads")
+
+    def export_ema(self) -> Dict[str, np.ndarray]:
+        out = {}
+        if self.conf.use_bn:
+            for l in range(1, len(self.conf.layers) + 1):
+                for nm in ("mean", "var"):
+                    t = self.ema_tensor(f"bn{l}_ema_{nm}").cpu().numpy()
+                    out[f"bn{l}_q_ema_{nm}"], out[f"bn{l}_d_ema_{nm}"] = t[0].copy(), t[1].copy()
+        return out
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        """Everything tf.train.Saver() would hold (new_dssm.py:248): trainables, EMA shadows, Adam slots."""
+        sd = {f"params/{k}": v for k, v in self._export("params").items()}
+        sd.update({f"adam_m/{k}": v for k, v in self._export("m").items()})
+        sd.update({f"adam_v/{k}": v for k, v in self._export("v").items()})
+        sd.update({f"ema/{k}": v for k, v in self.export_ema().items()})
+        sd["beta_pow"] = self.beta_pow.cpu().numpy().copy()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, np.ndarray]) -> None:
+        self.load_params({k[len("params/"):]: v for k, v in sd.items() if k.startswith("params/")})
+        n = len(self.conf.layers)
+        for slot, which in (("adam_m", "m"), ("adam_v", "v")):
+            for l in range(1, n + 1):
+                self.param(f"W{l}", which).copy_(torch.from_numpy(sd[f"{slot}/W{l}"]))
+                self.param(f"b{l}", which).copy_(torch.from_numpy(sd[f"{slot}/b{l}"]).view(1, -1))
+                if self.conf.use_bn:
+                    for w in ("gamma", "beta"):
+                        st = np.stack([sd[f"{slot}/bn{l}_q_{w}"], sd[f"{slot}/bn{l}_d_{w}"]]).astype(np.float32)
+                        self.param(f"bn{l}_{w}", which).copy_(torch.from_numpy(st))
+        if self.conf.use_bn:
+            for l in range(1, n + 1):
+                for nm in ("mean", "var"):
+                    st = np.stack([sd[f"ema/bn{l}_q_ema_{nm}"], sd[f"ema/bn{l}_d_ema_{nm}"]]).astype(np.float32)
+                    self.ema_tensor(f"bn{l}_ema_{nm}").copy_(torch.from_numpy(st))
+        self.beta_pow.copy_(torch.from_numpy(np.asarray(sd["beta_pow"], dtype=np.float32)))
+
+    # ---- execution ------------------------------------------------------------------------------------
+    def _check_batch(self, x: DeviceCSR):
+        if x.rows != self.conf.rows:
+            raise ValueError(f"batch has {x.rows} rows, the graph needs exactly (2+NEG)*query_BS = {self.conf.rows}")
+        if x.n_cols != self.conf.TRIGRAM_D:
+            raise ValueError("batch TRIGRAM_D mismatch")
+        if x.nnz > self.max_nnz:
+            raise ValueError(f"batch nnz {x.nnz} exceeds max_nnz {self.max_nnz} the tower was sized for")
+
+    def to_device(self, b: StackedBatch) -> DeviceCSR:
+        return DeviceCSR.from_host(b, self.device)
+
+    def forward(self, x: DeviceCSR, on_train: bool = False, update_ema: Optional[bool] = None) -> torch.Tensor:
+        """sess.run(loss, feed) -- new_dssm.py:276-278.  Returns the device loss scalar; other tensors via tensor()."""
+        self._check_batch(x)
+        ue = on_train if update_ema is None else update_ema
+        check(lib.dssm_tower_forward(self._h, ptr(x.indptr), ptr(x.indices), ptr(x.values), int(on_train), int(ue), stream_ptr()))
+        self._last = x  # keep the CSR alive for backward
+        return self.tensor("loss")
+
+    def backward(self) -> None:
+        check(lib.dssm_tower_backward(self._h, stream_ptr()))
+
+    def adam(self, grad_scale: float = 1.0) -> None:
+        check(lib.dssm_tower_adam(self._h, float(grad_scale), stream_ptr()))
+
+    def train_step(self, x: DeviceCSR) -> torch.Tensor:
+        """sess.run(train_step, feed_dict=pull_batch(True, ...)) -- new_dssm.py:267-269.  Device CSR in, device loss out."""
+        self._check_batch(x)
+        check(lib.dssm_tower_train_step(self._h, ptr(x.indptr), ptr(x.indices), ptr(x.values), stream_ptr()))
+        self._last = x
+        return self.tensor("loss")
+
+    # host-buffer path (what a caller holding scipy/numpy batches uses; bench.py's e2e)
+    def pin(self, b: StackedBatch):
+        """Pinned host copies of a stacked batch (for asynchronous upload)."""
+        return (torch.from_numpy(b.indptr).pin_memory(), torch.from_numpy(b.indices).pin_memory(),
+                torch.from_numpy(b.values).pin_memory(), b.nnz)
+
+    def capture_graph(self) -> None:
+        """Capture forward+backward+Adam on the staging CSR into a CUDA graph (replayed by train_step_host)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            check(lib.dssm_tower_capture_graph(self._h, s.cuda_stream))
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self._graph = True
+
+    def stage(self, x: DeviceCSR) -> None:
+        """Device-to-device copy of a batch into the staging CSR (bench.py's device-resident `value` leg)."""
+        self._check_batch(x)
+        ip, ix, vl = self.staging_views()
+        ip.copy_(x.indptr)
+        ix[:x.nnz].copy_(x.indices)
+        vl[:x.nnz].copy_(x.values)
+
+    def staging_views(self):
+        """torch views over the staging CSR inside the workspace (indptr, indices, values)."""
+        ip, ix, vl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib.dssm_tower_staging(self._h, C.byref(ip), C.byref(ix), C.byref(vl)))
+        base = self.workspace.data_ptr()
+        R = self.conf.rows
+        w32 = self.workspace.view(torch.int32)
+        o = lambda p: (p.value - base) // 4
+        return (w32[o(ip):o(ip) + R + 1], w32[o(ix):o(ix) + self.max_nnz],
+                self._ws_f32[o(vl):o(vl) + self.max_nnz])
+
+    def train_step_staged(self) -> torch.Tensor:
+        check(lib.dssm_tower_train_step_staged(self._h, stream_ptr()))
+        return self.tensor("loss")
+
+    def train_step_host(self, pinned, read_loss: bool = True) -> Optional[float]:
+        """One step from HOST buffers: H2D of the CSR, the step, D2H of the loss (synchronises when read_loss)."""
+        indptr, indices, values, nnz = pinned
+        hl = ptr(self._host_loss) if read_loss else None
+        check(lib.dssm_tower_train_step_host(self._h, ptr(indptr), ptr(indices), ptr(values), nnz, hl, stream_ptr()))
+        return float(self._host_loss[0]) if read_loss else None
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.dssm_tower_launch_count(self._h))
+
+    # ---- sess.run shim --------------------------------------------------------------------------------
+    def run(self, fetches, feed_dict: Dict):
+        """tower.run('train_step' | 'loss' | 'BN2/embedding_query_y:0' | [...], feed_dict=pull_batch(...))."""
+        single = isinstance(fetches, str)
+        names = [fetches] if single else list(fetches)
+        x = self.to_device(stack_feed(feed_dict, self.conf))
+        on_train = bool(feed_dict.get(ON_TRAIN, False))
+        if any(n.split("/")[-1].split(":")[0] == "train_step" for n in names):
+            self.train_step(x)
+        else:
+            self.forward(x, on_train=on_train)
+        out = []
+        for n in names:
+            key = n.split("/")[-1].split(":")[0]
+            out.append(None if key == "train_step" else self.tensor(n).detach().cpu().numpy().copy())
+        return out[0] if single else out

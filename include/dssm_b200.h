@@ -1,0 +1,263 @@
+/*
+ * dssm_b200.h -- C ABI of the B200-native DSSM two-tower hot path.
+ *
+ * The reference (MC-Zealot/dssm) has no FFI: its "interface" is a flat TensorFlow-1.x script
+ * (semantic_matching/dssm/new_dssm.py) whose arithmetic lives in TF op kernels.  Every entry point
+ * below therefore names the reference *call site* (file:line under /root/reference) whose TF ops it
+ * replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions:
+ *   - extern "C", plain pointers and sizes; all data pointers are DEVICE pointers unless the
+ *     parameter name starts with `host_`.
+ *   - every call returns int: 0 = DSSM_OK, otherwise one of DSSM_ERR_*; dssm_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - no hidden device allocation: ops that need scratch take (workspace, workspace_bytes) and have a
+ *     *_workspace_bytes() query.  Workspaces must be 256-byte aligned.
+ *   - every call takes a stream (a cudaStream_t passed as void*); nothing synchronises the host
+ *     except the *_host entry points, which say so.
+ *   - a dssm_tower handle is not thread-safe: one handle per device/stream.
+ *   - float tensors are fp32 row-major; index tensors are int32.
+ *
+ * Row convention for a batch (utils/utils.py:45-61, pull_batch): the three CSR slices are stacked
+ *   rows [0,B)            query_batch
+ *   rows [B,2B)           doc_positive_batch
+ *   rows [2B,2B+B*NEG)    doc_negative_batch  (negatives of query j are rows 2B + j*NEG .. +NEG-1)
+ * R = (2+NEG)*B rows in total.  "Segment" below: q = rows [0,B), d = rows [B,R)  (the two
+ * batch_normalization instances of new_dssm.py:129-130 / :151-152).
+ */
+#ifndef DSSM_B200_H_
+#define DSSM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSSM_B200_VERSION 100
+
+typedef void* dssm_stream_t; /* cudaStream_t */
+
+enum {
+    DSSM_OK = 0,
+    DSSM_ERR_BAD_ARG = 1,   /* null pointer / negative size / unknown enum */
+    DSSM_ERR_BAD_SHAPE = 2, /* shape not supported by the kernels */
+    DSSM_ERR_BAD_ALIGN = 3, /* pointer not 16-byte aligned where vector access needs it */
+    DSSM_ERR_CUDA = 4,      /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    DSSM_ERR_WORKSPACE = 5, /* workspace too small */
+    DSSM_ERR_STATE = 6      /* tower used before bind / backward before forward ... */
+};
+
+enum { DSSM_ACT_NONE = 0, DSSM_ACT_RELU = 1, DSSM_ACT_TANH = 2 };
+
+/* Arithmetic of the dense-layer contractions (FC2.. and their gradients).
+ *   FP32   : FFMA, fp32 accumulate -- the 1e-5 parity mode.
+ *   BF16_TC: tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate in TMEM) -- stated tolerance. */
+enum { DSSM_GEMM_FP32 = 0, DSSM_GEMM_BF16_TC = 1 };
+
+#define DSSM_MAX_LAYERS 8
+
+/* Hyper-parameters; names follow semantic_matching/dssm/config.py:19-28 and new_dssm.py:44. */
+typedef struct dssm_config {
+    int32_t TRIGRAM_D;               /* input vocabulary size (new_dssm.py:44) */
+    int32_t n_layers;                /* 2 in the reference graph (L1_N, L2_N); 3 for 300-300-128 */
+    int32_t layers[DSSM_MAX_LAYERS]; /* L1_N, L2_N, ... */
+    int32_t NEG;                     /* config.py:28 */
+    int32_t query_BS;                /* config.py:19 */
+    int32_t use_bn;                  /* 1: semantic_matching/dssm, 0: semantic_matching/dssm_no_bn */
+    int32_t act;                     /* DSSM_ACT_RELU (reference) or DSSM_ACT_TANH */
+    int32_t loss_div_bs;             /* 1: new_dssm.py:209, 0: archive/dssm_v2.py:184 */
+    int32_t gemm_mode;               /* DSSM_GEMM_* */
+    float bn_eps;                    /* 1e-3, new_dssm.py:87 */
+    float ema_decay;                 /* 0.5, new_dssm.py:78 */
+    float gamma;                     /* 20, new_dssm.py:199 */
+    float loss_eps;                  /* 0 (new_dssm.py:209) or 1e-8 (dssm_no_bn/my_dssm.py:169) */
+    float learning_rate;             /* config.py:23 */
+    float beta1, beta2, adam_eps;    /* tf.train.AdamOptimizer defaults .9 .999 1e-8 (new_dssm.py:217) */
+} dssm_config;
+
+const char* dssm_last_error(void);
+int dssm_version(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+int dssm_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * FC1: word-hashed sparse input layer.   Replaces tf.sparse_tensor_dense_matmul(x, weight1) + bias1
+ * (new_dssm.py:124-126) for the three stacked inputs at once.
+ *   Y[r,:] = sum_{p in [indptr[r],indptr[r+1])} values[p] * W1[indices[p],:]  (+ b1)
+ * CSR must be canonical (sorted, duplicate-free columns per row).  b1 may be NULL.
+ * W1/b1/Y must be 16-byte aligned when L1 % 4 == 0 (vector path).
+ */
+int dssm_spmm_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
+                  const float* W1, const float* b1, int32_t L1, float* Y, dssm_stream_t stream);
+
+/* Gradient of FC1 w.r.t. weight1: the dense [D,L1] tensor  dW1 = X^T dH  that TF's
+ * SparseTensorDenseMatMul gradient (adjoint_a=True) produces for new_dssm.py:124-126, summed over
+ * the three tower applications.  Every row of dW1 is written (rows of absent columns are zero).
+ * method 0: per-batch CSC built on device + gather-by-column (each dW1 row written once),
+ * method 1: zero-fill + red.global.add.v4.f32 scatter (kept as the cross-check). */
+size_t dssm_spmm_bwd_dw_workspace_bytes(int32_t R, int32_t D, int32_t L1, int64_t max_nnz);
+int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
+                     const float* dH, int32_t L1, float* dW1, int32_t method, void* workspace,
+                     size_t workspace_bytes, dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
+ * (query segment rows [0,B), doc segment rows [B,R)) in one call.
+ * All per-column vectors are laid out [2][L]: index 0 = query instance, 1 = doc instance.
+ *   on_train != 0: mean/var = batch moments (biased variance, tf.nn.moments); if update_ema the
+ *                  shadows move: ema -= (1-decay)*(ema - batch)            (new_dssm.py:78-83)
+ *   on_train == 0: mean/var = shadows                                       (new_dssm.py:85-86)
+ *   out: mean,var,rstd = rsqrt(var+eps), scale = gamma*rstd, shift = beta - mean*scale  (:87)
+ * The normalised tensor itself is not written: consumers apply act(x*scale+shift) on load.
+ */
+size_t dssm_bn_workspace_bytes(int32_t R, int32_t L);
+int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, int32_t on_train, int32_t update_ema,
+                    const float* gamma, const float* beta, float* ema_mean, float* ema_var, float eps,
+                    float ema_decay, float* mean, float* var, float* rstd, float* scale, float* shift,
+                    void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+
+/* Y = act(X*scale + shift) per segment (tf.nn.batch_normalization + tf.nn.relu, new_dssm.py:87,
+ * :134-136, :156-158).  scale/shift NULL = identity (dssm_no_bn/my_dssm.py:98-121). */
+int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B, const float* scale, const float* shift,
+                      int32_t act, float* Y, dssm_stream_t stream);
+
+/* Backward of act(BN(x)) for one layer.  In: dA = dLoss/d(post-activation) [R,L] ; H = pre-BN
+ * activations saved by the forward.  Out (in place over dA): dH = dLoss/dH; dgamma,dbeta [2][L].
+ * With scale == NULL (no-BN mode) only the activation derivative is applied. */
+int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act,
+                         const float* gamma, const float* mean, const float* rstd, const float* scale,
+                         const float* shift, float* dgamma, float* dbeta, void* workspace,
+                         size_t workspace_bytes, dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FC2..: dense layer.  Replaces tf.matmul(x_out, weight2) + bias2 for the three inputs
+ * (new_dssm.py:146-148) with the previous layer's BN + activation fused into the A-operand load:
+ *   Hout[R,N] = act(Hprev*scale + shift)[R,K] . W[K,N] + bias[N]
+ * scale/shift are [2][K] (per segment) or NULL (identity); act applies also when scale is NULL.
+ */
+int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                int32_t act, const float* W, const float* bias, int32_t N, float* Hout, int32_t gemm_mode,
+                dssm_stream_t stream);
+/* dA[R,K] = dH[R,N] . W[K,N]^T   (gradient w.r.t. the post-activation input of the layer) */
+int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
+                   int32_t gemm_mode, dssm_stream_t stream);
+/* dW[K,N] = act(Hprev*scale+shift)^T . dH ;  db[N] = column sums of dH.  Deterministic split-K. */
+size_t dssm_fc_bwd_dw_workspace_bytes(int32_t R, int32_t K, int32_t N);
+int dssm_fc_bwd_dw(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                   int32_t act, const float* dH, int32_t N, float* dW, float* db, int32_t gemm_mode,
+                   void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+/* out[N] = column sums of X[R,N] (bias gradient of FC1). Deterministic. */
+size_t dssm_colsum_workspace_bytes(int32_t R, int32_t N);
+int dssm_colsum(const float* X, int32_t R, int32_t N, float* out, void* workspace, size_t workspace_bytes,
+                dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Merge_Negative_Doc (new_dssm.py:160-180): doc_y = [doc_positive_y ; negatives in slot-major order]
+ *   doc_y[r] = pos[r] (r < B);  doc_y[(i+1)*B + j] = neg[j*NEG + i].
+ * The index form writes src[r] = source row in the stacked [pos ; neg] matrix (bit-exact contract).
+ */
+int dssm_merge_negative_doc(const float* doc_positive_y, const float* doc_negative_y, int32_t B, int32_t NEG,
+                            int32_t L, float* doc_y, dssm_stream_t stream);
+int dssm_merge_negative_doc_index(int32_t B, int32_t NEG, int32_t* src, dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cosine_Similarity + Loss (new_dssm.py:182-213) and their gradient, one warp per query group.
+ * Y [R,L] = stacked embeddings (query_y ; doc_positive_y ; doc_negative_y), post-activation.
+ * Outputs (any may be NULL except loss_terms):
+ *   query_norm_single [B]            (:187)
+ *   doc_norm   [(1+NEG)*B]           (:190)   reference order: row k*B + j
+ *   cos_sim_raw[(1+NEG)*B]           (:197)   reference order: row k*B + j   (0/0 -> NaN, no epsilon)
+ *   cos_sim    [B,(1+NEG)]           (:199)   = gamma * raw
+ *   prob       [B,(1+NEG)]           (:206)   max-subtracted softmax
+ *   loss_terms [B]                   -log(prob[j,0] + loss_eps)
+ *   loss       [1]                   sum(loss_terms) / (loss_div_bs ? B : 1)   (:209)
+ *   dY         [R,L]                 dLoss/dY, same stacked row order as Y (NULL = forward only)
+ */
+int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int32_t L, float gamma, float loss_eps,
+                          int32_t loss_div_bs, float* query_norm_single, float* doc_norm, float* cos_sim_raw,
+                          float* cos_sim, float* prob, float* loss_terms, float* loss, float* dY,
+                          dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training (new_dssm.py:215-217): tf.train.AdamOptimizer over one flat parameter buffer.
+ *   beta_pow[2] (device) holds beta1^t, beta2^t (initialised to beta1, beta2);
+ *   lr_t = lr*sqrt(1-b2p)/(1-b1p); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t m/(sqrt(v)+eps)
+ *   g = grads * grad_scale (1/world_size after a summing all-reduce).
+ * dssm_adam_advance multiplies the powers by beta1, beta2 (TF does it after all variables' updates).
+ */
+int dssm_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const float* beta_pow,
+                   float lr, float beta1, float beta2, float eps, float grad_scale, dssm_stream_t stream);
+int dssm_adam_advance(float* beta_pow, float beta1, float beta2, dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Corpus cosine top-k.  No reference function exists; cosine follows
+ * new_dssm.py:185-197 (no epsilon), ordering follows tf.nn.top_k(sorted=True)
+ * (utils/tf_ranking_utils.py:47): score descending, ties to the lower doc id; NaN ranks as -inf.
+ * Scores use the sequential fp32 multiply-then-add of oracle/retrieval_oracle.py so ids are bit-exact.
+ *   out_scores [nq,k] fp32, out_ids [nq,k] int32 (= id_offset + local row), sorted.
+ * dssm_topk_merge merges n_parts per-shard results laid out [n_parts][nq][k] into the global top-k.
+ */
+size_t dssm_corpus_topk_workspace_bytes(int32_t nq, int64_t nd, int32_t d, int32_t k);
+int dssm_corpus_topk(const float* Q, int32_t nq, const float* docs, int64_t nd, int32_t d, int32_t k,
+                     int32_t id_offset, float* out_scores, int32_t* out_ids, void* workspace,
+                     size_t workspace_bytes, dssm_stream_t stream);
+int dssm_topk_merge(const float* part_scores, const int32_t* part_ids, int32_t n_parts, int32_t nq, int32_t k,
+                    float* out_scores, int32_t* out_ids, dssm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tower handle: the whole graph of new_dssm.py:104-217 over caller-owned device buffers.
+ *
+ * Flat parameter layout (all offsets in floats, each tensor padded to a multiple of 4 floats):
+ *   for l = 1..n_layers:  W{l} [in,out], b{l} [out]
+ *   if use_bn: for l = 1..n_layers:  bn{l}_gamma [2][out], bn{l}_beta [2][out]   (0 = query, 1 = doc)
+ * grads / m / v use the same layout.  ema: for l: bn{l}_ema_mean [2][out], bn{l}_ema_var [2][out].
+ * dssm_tower_tensor_info enumerates it (kind 0 = params/grads/m/v, 1 = ema, 2 = workspace tensors of
+ * the last forward: h{l}, Y, dY, cos_sim_raw, query_norm_single, doc_norm, cos_sim, prob, loss_terms, loss,
+ * bn{l}_mean/var/rstd/scale/shift).
+ */
+typedef struct dssm_tower dssm_tower;
+
+int dssm_tower_create(const dssm_config* cfg, dssm_tower** out);
+void dssm_tower_destroy(dssm_tower* t);
+int64_t dssm_tower_param_count(const dssm_tower* t); /* floats in params (= grads = m = v) */
+int64_t dssm_tower_ema_count(const dssm_tower* t);   /* floats in ema */
+size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nnz);
+int32_t dssm_tower_num_tensors(const dssm_tower* t, int32_t kind);
+int dssm_tower_tensor_info(const dssm_tower* t, int32_t kind, int32_t index, char* name, int32_t name_cap,
+                           int64_t* offset_floats, int64_t* rows, int64_t* cols);
+/* beta_pow: 2 floats (device) initialised by the caller to {beta1, beta2}. */
+int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float* m, float* v, float* ema, float* beta_pow,
+                    void* workspace, size_t workspace_bytes, int64_t max_nnz);
+/* sess.run(loss / embeddings, feed_dict=pull_batch(on_train, ...)) -- new_dssm.py:276-285,
+ * load_model_and_save_vector.py:60-99.  Device CSR of the stacked batch. */
+int dssm_tower_forward(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                       int32_t on_train, int32_t update_ema, dssm_stream_t stream);
+/* Gradients of `loss` w.r.t. every trainable into the bound grads buffer (training-mode forward must
+ * precede it with the same CSR pointers still valid). */
+int dssm_tower_backward(dssm_tower* t, dssm_stream_t stream);
+/* Adam on the bound buffers; grad_scale multiplies the grads first (data-parallel average). */
+int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t stream);
+/* sess.run(train_step, feed_dict=pull_batch(True, ...)) -- new_dssm.py:267-269: forward + backward + Adam. */
+int dssm_tower_train_step(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
+                          dssm_stream_t stream);
+/* Same with HOST CSR buffers (pinned for async copies): uploads into the workspace staging area, runs the
+ * step and copies the loss back; synchronises the stream before returning.  host_loss may be NULL
+ * (then no readback and no synchronisation). */
+int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                               const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream);
+/* Capture forward+backward+Adam over the bound buffers into a CUDA graph reading the CSR from the
+ * workspace staging area; afterwards dssm_tower_train_step_host / _staged replay the graph. */
+int dssm_tower_capture_graph(dssm_tower* t, dssm_stream_t stream);
+/* Device pointers of the staging CSR (indptr [R+1], indices [max_nnz], values [max_nnz]). */
+int dssm_tower_staging(dssm_tower* t, int32_t** indptr, int32_t** indices, float** values);
+/* Run one train step on whatever is in the staging CSR (graph replay when captured). */
+int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream);
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t dssm_tower_launch_count(const dssm_tower* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSSM_B200_H_ */
