@@ -47,10 +47,10 @@ class dssm_config(C.Structure):
 
 
 def _load() -> C.CDLL:
-    if not LIB_PATH.exists() or os.environ.get("DSSM_B200_REBUILD") == "1":
-        from .build import build  # needs nvcc; raises if absent
+    from . import build as _build
 
-        build(force=os.environ.get("DSSM_B200_REBUILD") == "1")
+    if os.environ.get("DSSM_B200_REBUILD") == "1" or not _build.up_to_date():
+        _build.build(force=os.environ.get("DSSM_B200_REBUILD") == "1")  # needs nvcc; raises if absent
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} is missing and could not be built; dssm_b200 has no CPU fallback")
     return C.CDLL(str(LIB_PATH))
@@ -103,6 +103,7 @@ SIGNATURES = {
     "dssm_tower_staging": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "dssm_tower_train_step_staged": (C.c_int, [_p, _p]),
     "dssm_tower_launch_count": (_i64, [_p]),
+    "dssm_tower_profile_step": (C.c_int, [_p, C.POINTER(C.c_float), _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -18,6 +18,26 @@ NVCC_FLAGS = [
 ]
 
 
+HASH_FILE = LIBDIR / "libdssm_b200.hash"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dssm_b200.h"]
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def up_to_date() -> bool:
+    return LIB.exists() and HASH_FILE.exists() and HASH_FILE.read_text().strip() == source_hash()
+
+
 def nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
@@ -34,6 +54,8 @@ def _stale(out: Path, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
+    if not force and not verbose and up_to_date():
+        return LIB
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     headers = [CSRC / "common.cuh", PKG.parent / "include" / "dssm_b200.h"] + sorted(CSRC.glob("*.cuh"))
@@ -42,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         s = CSRC / src
         o = objdir / (s.stem + ".o")
         objs.append(o)
-        if force or _stale(o, [s, *headers]):
+        if force or not up_to_date() or _stale(o, [s, *headers]):
             cmd = [nvcc(), *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
@@ -60,6 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if force or procs or _stale(LIB, objs):
         cmd = [nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         subprocess.run(cmd, check=True)
+    HASH_FILE.write_text(source_hash())
     return LIB
 
 

@@ -365,6 +365,9 @@ static void launch_scatter(const int* indptr, const int* indices, const float* v
         default: { constexpr int N_ = 8; CALL; } break; \
     }
 
+// set by the tower's profiling step: recorded between the CSC build and the gather kernel
+thread_local cudaEvent_t g_spmm_bwd_mid_event = nullptr;
+
 }  // namespace dssm
 
 using namespace dssm;
@@ -454,6 +457,7 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
         csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.csc_row, w.csc_val);
         LAUNCH_CHECK("csc_fill");
     }
+    if (g_spmm_bwd_mid_event) CUDA_TRY(cudaEventRecord(g_spmm_bwd_mid_event, st));
     const int nch = cdiv(L1 / 4, 32);
     DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, st));
     LAUNCH_CHECK("dw_gather");

@@ -17,6 +17,23 @@ struct TensorInfo {
 
 static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
 
+extern thread_local cudaEvent_t g_spmm_bwd_mid_event;
+
+// phase boundaries of one profiled step (dssm_tower_profile_step)
+enum { PH_START = 0, PH_SPMM_FWD, PH_DENSE_FWD, PH_COSLOSS, PH_DENSE_BWD, PH_CSC_BUILD, PH_DW_GATHER, PH_B1, PH_ADAM, PH_COUNT };
+struct PhaseTimer {
+    cudaEvent_t ev[PH_COUNT];
+    cudaStream_t st;
+    bool on;
+    void mark(int i) {
+        if (on) cudaEventRecord(ev[i], st);
+    }
+};
+static thread_local PhaseTimer* g_timer = nullptr;
+static inline void mark(int i) {
+    if (g_timer) g_timer->mark(i);
+}
+
 }  // namespace dssm
 
 using namespace dssm;
@@ -251,7 +268,9 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
                               int on_train, int update_ema, bool want_grad, dssm_stream_t s) {
     const dssm_config& c = t->cfg;
     const int n = t->n_layers, R = t->R, B = t->B;
+    mark(PH_START);
     TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
+    mark(PH_SPMM_FWD);
     for (int l = 1; l <= n; ++l) {
         const std::string ls = std::to_string(l);
         if (c.use_bn) {
@@ -270,8 +289,10 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
             TRY(dssm_bn_act_apply(t->h[l], R, t->L[l], B, sc, sh, c.act, t->Y, s));
         }
     }
+    mark(PH_DENSE_FWD);
     TRY(dssm_cos_softmax_loss(t->Y, B, t->NEG, t->L[n], c.gamma, c.loss_eps, c.loss_div_bs, t->qnorm, t->dnorm,
                               t->cos_raw, t->cos_sim, t->prob, t->loss_terms, t->loss, want_grad ? t->dh[n] : nullptr, s));
+    mark(PH_COSLOSS);
     t->cur_indptr = indptr; t->cur_indices = indices; t->cur_values = values;
     t->fwd_train_done = want_grad && on_train;
     return DSSM_OK;
@@ -297,9 +318,15 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s) {
                                t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
             TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, s));
         } else {
-            TRY(dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1], t->G_("W1"), 0,
-                                 t->sp_ws, t->sp_ws_bytes, s));
+            mark(PH_DENSE_BWD);
+            if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];
+            const int rc = dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1],
+                                            t->G_("W1"), 0, t->sp_ws, t->sp_ws_bytes, s);
+            g_spmm_bwd_mid_event = nullptr;
+            TRY(rc);
+            mark(PH_DW_GATHER);
             TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
+            mark(PH_B1);
         }
     }
     return DSSM_OK;
@@ -426,3 +453,32 @@ extern "C" int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_ind
 }
 
 extern "C" int64_t dssm_tower_launch_count(const dssm_tower* t) { return t ? t->launches : -1; }
+
+extern "C" int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && host_phase_ms, DSSM_ERR_STATE, "dssm_tower_profile_step: tower not bound / null output");
+    DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_profile_step: optimizer buffers not bound");
+    PhaseTimer pt;
+    pt.st = (cudaStream_t)stream;
+    pt.on = true;
+    for (int i = 0; i < PH_COUNT; ++i) CUDA_TRY(cudaEventCreate(&pt.ev[i]));
+    g_timer = &pt;
+    int rc;
+    {
+        LaunchScope ls(t);
+        rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
+        if (rc == DSSM_OK) mark(PH_ADAM);
+    }
+    g_timer = nullptr;
+    if (rc == DSSM_OK) {
+        cudaError_t e = cudaStreamSynchronize(pt.st);
+        if (e != cudaSuccess) rc = fail(DSSM_ERR_CUDA, "profile step failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == DSSM_OK)
+        for (int i = 1; i < PH_COUNT; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pt.ev[i - 1], pt.ev[i]);
+            host_phase_ms[i - 1] = ms;
+        }
+    for (int i = 0; i < PH_COUNT; ++i) cudaEventDestroy(pt.ev[i]);
+    return rc;
+}

@@ -277,6 +277,14 @@ class DSSMTower:
         check(lib.dssm_tower_train_step_host(self._h, ptr(indptr), ptr(indices), ptr(values), nnz, hl, stream_ptr()))
         return float(self._host_loss[0]) if read_loss else None
 
+    PHASES = ("spmm_fwd", "dense_fwd", "cos_loss", "dense_bwd", "csc_build", "dw_gather", "db1", "adam")
+
+    def profile_step(self) -> Dict[str, float]:
+        """One un-graphed step on the staging CSR with CUDA events between phases -> {phase: ms}. Synchronises."""
+        buf = (C.c_float * 8)()
+        check(lib.dssm_tower_profile_step(self._h, buf, stream_ptr()))
+        return {k: float(buf[i]) for i, k in enumerate(self.PHASES)}
+
     @property
     def launch_count(self) -> int:
         return int(lib.dssm_tower_launch_count(self._h))

@@ -256,6 +256,9 @@ int dssm_tower_staging(dssm_tower* t, int32_t** indptr, int32_t** indices, float
 int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dssm_tower_launch_count(const dssm_tower* t);
+/* One un-graphed train step on the staging CSR with CUDA events between the phases; synchronises.
+ * host_phase_ms[8] = {FC1 SpMM fwd, dense fwd (BN+FC), cosine/loss, dense bwd, CSC build, dW1 gather, db1, Adam}. */
+int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,3 +76,65 @@ def to_stacked(X):
 
     X = sp.csr_matrix(X)
     return StackedBatch(X.indptr.astype(np.int32), X.indices.astype(np.int32), X.data.astype(np.float32), X.shape[1])
+
+
+def tf_adam_reference(p0, g, m0, v0, b1p, b2p, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """tf.train.AdamOptimizer's ApplyAdam in float64 with TF's fp32 scalars ((1-beta) is 1-float32(beta))."""
+    f = lambda x: float(np.float32(x))
+    b1, b2, lr, eps = f(beta1), f(beta2), f(lr), f(eps)
+    omb1, omb2 = float(np.float32(1) - np.float32(beta1)), float(np.float32(1) - np.float32(beta2))
+    g = np.asarray(g, np.float64) * grad_scale
+    m = b1 * np.asarray(m0, np.float64) + omb1 * g
+    v = b2 * np.asarray(v0, np.float64) + omb2 * g * g
+    lr_t = lr * np.sqrt(1 - float(b2p)) / (1 - float(b1p))
+    return np.asarray(p0, np.float64) - lr_t * m / (np.sqrt(v) + eps), m, v
+
+
+def assert_update_close(got, ref, init, use_bn, what="", l2_tol=2e-2):
+    """Parameters after Adam steps, compared as the relative L2 error of the *update* (got-ref vs ref-init).
+    An element-wise max-norm check is ill-posed here for ANY two fp32 implementations (TF-CPU vs TF-GPU included):
+    Adam divides by sqrt(v)+1e-8, so for the many W entries whose gradient is below ~1e-6 the update is
+    lr*g/3e-7 -- fp32 summation noise of 1e-9 in g moves the weight by 3e-5, i.e. 0.2 % of the weight scale --
+    and under BN the pre-BN biases b{l} have an analytically ZERO gradient, so their update is pure rounding noise
+    (they are skipped; BN removes them from the function).  The Adam arithmetic itself is pinned separately, to
+    1e-6, by applying the TF formula on the host to the GPU's own gradients (test_gpu_tower.py)."""
+    for k in ref:
+        if use_bn and k[0] == "b" and k[1:].isdigit():
+            continue
+        g, r, i0 = np.asarray(got[k], np.float64), np.asarray(ref[k], np.float64), np.asarray(init[k], np.float64)
+        assert g.shape == r.shape, k
+        upd = np.linalg.norm((r - i0).ravel())
+        if upd > 0:
+            rel = np.linalg.norm((g - r).ravel()) / upd
+            assert rel <= l2_tol, f"{what} {k}: update differs by {rel:.2e} in relative L2"
+
+
+def grad_tolerances(conf, X, params, tol=5e-5):
+    """Reference gradients in float64 plus, per tensor, the error the NumPy fp32 port itself makes against them.
+    A GPU gradient passes if it is within `tol` of the tensor scale OR within 4x the fp32 port's own error
+    (reductions with cancellation, e.g. BN beta/gamma sums over thousands of rows, are noise-limited for every
+    fp32 implementation)."""
+    from oracle import DSSMOracle
+
+    o64 = DSSMOracle(oracle_config(conf), params, dtype=np.float64)
+    c64 = o64.forward(X, on_train=True, update_ema=False)
+    g64 = o64.backward(c64)
+    o32 = DSSMOracle(oracle_config(conf), params, dtype=np.float32)
+    c32 = o32.forward(X, on_train=True, update_ema=False)
+    g32 = o32.backward(c32)
+    allow = {}
+    for k in g64:
+        scale = max(np.abs(g64[k]).max(), 1e-30)
+        allow[k] = max(tol * scale, 4 * np.abs(g32[k].astype(np.float64) - g64[k]).max())
+    return g64, allow, c64
+
+
+def assert_grads_close(conf, got, g64, allow, c64):
+    for k, ref in g64.items():
+        if conf.use_bn and k[0] == "b" and k[1:].isdigit():
+            # analytically zero under BN; what is left is summation noise of dh{l}'s columns
+            bound = 1e-5 * float(np.abs(c64["dh" + k[1:]]).sum(axis=0).max())
+            assert np.abs(got[k] - ref).max() <= bound, f"grad {k} (zero under BN): {np.abs(got[k] - ref).max():.3e} > {bound:.3e}"
+            continue
+        err = np.abs(np.asarray(got[k], np.float64) - ref).max()
+        assert err <= allow[k], f"grad {k}: abs error {err:.3e} > allowed {allow[k]:.3e} (scale {np.abs(ref).max():.3e})"

@@ -316,16 +316,19 @@ def test_adam_three_steps_vs_tf_formula(n):
     ref = p.astype(np.float64)
     P, M, V = dev(p), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
     bp = torch.tensor([0.9, 0.999], device="cuda")
-    b1p, b2p = 0.9, 0.999
+    # TF's ApplyAdam works on fp32 scalars: (1 - beta2) is 1 - float32(0.999), 1.3e-5 away from 0.001
+    b1, b2, lr, eps = (float(np.float32(x)) for x in (0.9, 0.999, 0.01, 1e-8))
+    omb1, omb2 = float(np.float32(1) - np.float32(0.9)), float(np.float32(1) - np.float32(0.999))
+    b1p, b2p = b1, b2
     for step in range(3):
         g = rng.standard_normal(n).astype(np.float32)
         g[::7] = 0
         ops.adam_step(P, dev(g), M, V, bp, 0.01, grad_scale=0.5)
         ge = 0.5 * g.astype(np.float64)
-        m = 0.9 * m + 0.1 * ge
-        v = 0.999 * v + 0.001 * ge * ge
-        ref = ref - 0.01 * np.sqrt(1 - b2p) / (1 - b1p) * m / (np.sqrt(v) + 1e-8)
-        b1p, b2p = b1p * 0.9, b2p * 0.999
+        m = b1 * m + omb1 * ge
+        v = b2 * v + omb2 * ge * ge
+        ref = ref - lr * np.sqrt(1 - b2p) / (1 - b1p) * m / (np.sqrt(v) + eps)
+        b1p, b2p = float(np.float32(b1p * b1)), float(np.float32(b2p * b2))
     assert_close(P.cpu().numpy(), ref, TOL, "adam params")
     assert_close(M.cpu().numpy(), m, TOL, "adam m")
     assert_close(V.cpu().numpy(), v, TOL, "adam v")
