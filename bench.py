@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- DSSM train step (fwd + bwd + TF-Adam) throughput in query-groups/s on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference graph (oracle)
+
+One "step" = one pass of the hot path (new_dssm.py:104-217: FC1 SpMM -> BN/FC stack -> Merge_Negative_Doc ->
+cosine/softmax/loss -> backward -> Adam over all parameters) over one synthetic batch of query_BS groups per GPU.
+Workload: BASELINE.json configs[1] = C2 (TRIGRAM_D=49284, 300-300-128, NEG=4, query_BS=1024 per GPU); N>1 is
+data-parallel with the same per-GPU batch (weak scaling) and an NCCL all-reduce of the flat gradient buffer.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train query-groups/s (q+1+NEG docs)"
+UNIT = "query-groups/s"
+
+
+def workload_conf(name: str, gemm_mode: str = "tc_3xtf32"):
+    from dssm_b200 import baseline_config
+
+    return baseline_config(name, gemm_mode)
+
+
+def describe(conf, name, n_gpus, extra=None):
+    d = {"workload": f"{name}: TRIGRAM_D={conf.TRIGRAM_D}, layers={'-'.join(map(str, conf.layers))}, NEG={conf.NEG}, "
+                     f"query_BS={conf.query_BS} per GPU, BN={'on' if conf.use_bn else 'off'}, fwd+bwd+Adam",
+         "query_BS_per_gpu": conf.query_BS, "global_query_BS": conf.query_BS * n_gpus, "NEG": conf.NEG,
+         "rows_per_step_per_gpu": conf.rows, "parallelism": f"dp{n_gpus}",
+         "l2_policy": "inputs larger than L2: every step streams W1+grads+Adam m,v (4 x 59 MB) plus a fresh batch; no explicit flush"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_port_step_time(conf, batches, params, steps: int, threads: int):
+    """The oracle (NumPy/SciPy restatement of new_dssm.py) timed on the host: `steps` full train steps."""
+    from oracle import DSSMOracle, OracleConfig
+
+    ocfg = OracleConfig(TRIGRAM_D=conf.TRIGRAM_D, layers=tuple(conf.layers), NEG=conf.NEG, query_BS=conf.query_BS,
+                        learning_rate=conf.learning_rate, use_bn=conf.use_bn, act=conf.act, loss_eps=conf.loss_eps,
+                        loss_div_bs=conf.loss_div_bs)
+    orc = DSSMOracle(ocfg, params)
+    Xs = [b.to_scipy() for b in batches]
+    orc.train_step(Xs[0])  # warm-up (BLAS thread pools, page faults)
+    times = []
+    for s in range(steps):
+        t0 = time.perf_counter()
+        orc.train_step(Xs[s % len(Xs)])
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: TensorFlow (the reference's engine) is not installable here, so the reference arm is the
+    CPU restatement of its graph (oracle/, kind 'port') on all host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dssm_b200.synthetic import init_params, make_batch
+
+    conf = workload_conf(args.workload)
+    batches = [make_batch(conf, seed=s) for s in range(2)]
+    params = init_params(conf, 0)
+    threads = host_threads()
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_port_step_time(conf, batches[:1], params, 0, threads)
+    times = cpu_port_step_time(conf, batches, params, args.steps, threads)
+    ms = 1e3 * float(np.mean(times))
+    value = conf.query_BS / (ms / 1e3)
+    sample = f"{args.steps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy port, single process"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": describe(conf, args.workload, 1, {"parallelism": "cpu"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(conf, nnz, P):
+    """SURVEY.md section 8(d) formulas, with the ACTUAL nnz of the generated batches."""
+    R, D, L1 = conf.rows, conf.TRIGRAM_D, conf.layers[0]
+    return {
+        "spmm_fwd": nnz * (4 * L1 + 8) + R * 4 * L1 + (R + 1) * 4,
+        "dw_gather": nnz * (4 * L1 + 8) + D * 4 * L1,
+        "adam": 28 * P,
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dssm_b200 import DSSMTower
+    from dssm_b200.parallel import DataParallelTower
+    from dssm_b200.synthetic import init_params, make_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    conf = workload_conf(args.workload, args.gemm_mode)
+    NB = 4  # distinct batches cycled through (each rank its own seeds)
+    batches = [make_batch(conf, seed=1000 * rank + s) for s in range(NB)]
+    max_nnz = max(b.nnz for b in batches)
+    mean_nnz = float(np.mean([b.nnz for b in batches]))
+    params = init_params(conf, 0)
+    tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params)
+    dev_batches = [tower.to_device(b) for b in batches]
+    pinned = [tower.pin(b) for b in batches]
+    dp = DataParallelTower(tower) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- leg 1: device-resident inputs ("value") ------------------------------------------------------
+    if world == 1:
+        tower.capture_graph()
+
+        def step(i):
+            tower.stage(dev_batches[i % NB])  # D2D copy of the batch into the staging CSR
+            tower.train_step_staged()  # CUDA-graph replay of fwd+bwd+Adam
+    else:
+        def step(i):
+            dp.train_step(dev_batches[i % NB])
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = tower.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = tower.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = conf.query_BS * world / (ms_per_step / 1e3)
+
+    # ---- leg 2: end to end from HOST buffers through the public API ("e2e") ---------------------------
+    if world == 1:
+        def e2e_step(i):
+            return tower.train_step_host(pinned[i % NB], read_loss=True)  # H2D CSR + step + D2H loss (+sync)
+    else:
+        host_loss = torch.zeros(1).pin_memory()
+
+        def e2e_step(i):
+            ip, ix, vl, nnz = pinned[i % NB]
+            sip, six, svl = tower.staging_views()
+            sip.copy_(ip, non_blocking=True)
+            six[:nnz].copy_(ix, non_blocking=True)
+            svl[:nnz].copy_(vl, non_blocking=True)
+            from dssm_b200.ops import DeviceCSR
+
+            x = DeviceCSR(sip, six, svl, conf.rows, conf.TRIGRAM_D, nnz)
+            loss = dp.train_step(x)
+            host_loss.copy_(loss.view(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host_loss[0])
+
+    for i in range(max(args.warmup, 1)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    last_loss = None
+    for i in range(args.steps):
+        last_loss = e2e_step(i)
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+    e2e_value = conf.query_BS * world / (e2e_ms / 1e3)
+    h2d = int(4 * (conf.rows + 1) + 8 * mean_nnz)
+
+    # ---- roofline: per-phase device time inside real (un-graphed) steps, CUDA events on the launch stream
+    roof = None
+    phases_avg = None
+    if rank == 0:
+        acc = {}
+        nprof = max(3, min(args.steps, 10))
+        for i in range(nprof + 2):
+            tower.stage(dev_batches[i % NB])
+            ph = tower.profile_step()
+            if i >= 2:
+                for k, v in ph.items():
+                    acc[k] = acc.get(k, 0.0) + v / nprof
+        phases_avg = acc
+        ab = algorithmic_bytes(conf, mean_nnz, tower.P)
+        kern = {k: {"ms": acc[k], "algorithmic_bytes": ab[k], "GBps": ab[k] / (acc[k] * 1e-3) / 1e9,
+                    "frac": ab[k] / (acc[k] * 1e-3) / 1e9 / hbm_peak} for k in ab}
+        dom = "spmm_fwd"  # the kernel north_star puts the >=70 %-of-HBM bar on
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        roof = {"kernel": "spmm_fwd_v4_kernel (FC1 CSR gather-accumulate)", "bound": "hbm", "achieved": kern[dom]["GBps"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": kern[dom]["ms"],
+                "other_kernels": {k: v for k, v in kern.items() if k != dom},
+                "phase_ms": acc, "phase_share_of_step": {k: v / sum(acc.values()) for k, v in acc.items()}}
+    if world > 1:
+        dist.barrier()
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores -----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        nsteps = 6 if conf.query_BS <= 1024 else 2
+        times = cpu_port_step_time(conf, batches[:2], params, nsteps, threads)
+        cpu = {"value": conf.query_BS / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{nsteps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy oracle "
+                         f"(scipy CSR @ is single-threaded, dense layers on OpenBLAS threads)",
+               "ms_per_step": 1e3 * float(np.mean(times))}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": describe(conf, args.workload, world, {"mean_nnz_per_step_per_gpu": mean_nnz, "gemm_mode": conf.gemm_mode,
+                                                               "distinct_batches": NB, "cuda_graph": world == 1}),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms, "last_loss": last_loss},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", help="C1 | C2 | C3 | C4 | C4_NOBN (per-GPU batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-mode", default="tc_3xtf32", choices=["fp32", "tc_3xtf32"],
+                    help="dense-layer arithmetic: FFMA fp32 or tcgen05 3xTF32 (both hold the 1e-5 parity bar)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded sample: the CPU port needs ~0.8 s per C2 step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

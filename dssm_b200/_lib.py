@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "lib" / "libdssm_b200.so"
 
 DSSM_OK = 0
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
-GEMM = {"fp32": 0, "bf16_tc": 1}
+GEMM = {"fp32": 0, "tc_3xtf32": 1}
 MAX_LAYERS = 8
 
 
@@ -72,7 +72,8 @@ SIGNATURES = {
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "dssm_bn_act_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "dssm_fc_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p]),
+    "dssm_fc_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dssm_fc_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
     "dssm_fc_bwd_dx": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p]),
     "dssm_fc_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dssm_fc_bwd_dw": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _i32, _p, _sz, _p]),

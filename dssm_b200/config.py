@@ -55,7 +55,13 @@ class Config(object):
 
 
 # BASELINE.json configs (C1..C4)
-def baseline_config(name: str) -> Config:
+def baseline_config(name: str, gemm_mode: str = "tc_3xtf32") -> Config:
+    c = _baseline_config(name)
+    c.gemm_mode = gemm_mode
+    return c
+
+
+def _baseline_config(name: str) -> Config:
     name = name.upper()
     if name == "C1":
         return Config(TRIGRAM_D=21128, query_BS=100, NEG=4, layers=(300, 300, 128))

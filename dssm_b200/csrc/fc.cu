@@ -195,16 +195,26 @@ static int pick_splits(int R) {
 using namespace dssm;
 
 // tcgen05 path (fc_tc.cu)
+extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N);
 extern "C" int dssm_fc_fwd_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t,
-                              const float*, const float*, int32_t, float*, dssm_stream_t);
+                              const float*, const float*, int32_t, float*, void*, size_t, dssm_stream_t);
+extern "C" int dssm_fc_bwd_dx_tc(const float*, int32_t, int32_t, const float*, int32_t, float*, dssm_stream_t);
+extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_t N);
+extern "C" int dssm_fc_bwd_dw_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t, const float*,
+                                 int32_t, float*, int32_t*, dssm_stream_t);
+
+extern "C" size_t dssm_fc_fwd_workspace_bytes(int32_t K, int32_t N, int32_t gemm_mode) {
+    return gemm_mode == DSSM_GEMM_TC_3XTF32 ? dssm_fc_tc_workspace_bytes(K, N) : 0;
+}
 
 extern "C" int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                            int32_t act, const float* W, const float* bias, int32_t N, float* Hout, int32_t gemm_mode,
-                           dssm_stream_t stream) {
+                           void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(Hprev && W && Hout, DSSM_ERR_BAD_ARG, "dssm_fc_fwd: null pointer");
     DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_fc_fwd: scale/shift must both be set or both NULL");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_fwd: bad shape R=%d K=%d N=%d", R, K, N);
-    if (gemm_mode == DSSM_GEMM_BF16_TC) return dssm_fc_fwd_tc(Hprev, R, K, B, scale, shift, act, W, bias, N, Hout, stream);
+    if (gemm_mode == DSSM_GEMM_TC_3XTF32)
+        return dssm_fc_fwd_tc(Hprev, R, K, B, scale, shift, act, W, bias, N, Hout, workspace, workspace_bytes, stream);
     DSSM_REQUIRE(gemm_mode == DSSM_GEMM_FP32, DSSM_ERR_BAD_ARG, "dssm_fc_fwd: unknown gemm_mode %d", gemm_mode);
     GemmArgs g{Hprev, W, Hout, bias, R, N, K, scale, shift, act, B, 0};
     dim3 grid(cdiv(N, BN), cdiv(R, BM), 1);
@@ -217,7 +227,7 @@ extern "C" int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float
                               int32_t gemm_mode, dssm_stream_t stream) {
     DSSM_REQUIRE(dH && W && dA, DSSM_ERR_BAD_ARG, "dssm_fc_bwd_dx: null pointer");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_bwd_dx: bad shape");
-    (void)gemm_mode;  // gradients stay on the fp32 path
+    if (gemm_mode == DSSM_GEMM_TC_3XTF32) return dssm_fc_bwd_dx_tc(dH, R, N, W, K, dA, stream);
     // C[R,K] = dH[R,N] . W[K,N]^T : reduce over N
     GemmArgs g{dH, W, dA, nullptr, R, K, N, nullptr, nullptr, DSSM_ACT_NONE, 0, 0};
     dim3 grid(cdiv(K, BN), cdiv(R, BM), 1);
@@ -248,7 +258,9 @@ extern "C" int dssm_colsum(const float* X, int32_t R, int32_t N, float* out, voi
 
 extern "C" size_t dssm_fc_bwd_dw_workspace_bytes(int32_t R, int32_t K, int32_t N) {
     if (R <= 0 || K <= 0 || N <= 0) return 0;
-    const size_t a = align_up((size_t)pick_splits(R) * K * N * sizeof(float), 256);
+    size_t a = align_up((size_t)pick_splits(R) * K * N * sizeof(float), 256);
+    const size_t t = dssm_fc_bwd_dw_tc_workspace_bytes(R, K, N);  // sized for either gemm_mode
+    if (t > a) a = t;
     return a + dssm_colsum_workspace_bytes(R, N);
 }
 
@@ -258,24 +270,29 @@ extern "C" int dssm_fc_bwd_dw(const float* Hprev, int32_t R, int32_t K, int32_t 
     DSSM_REQUIRE(Hprev && dH && dW, DSSM_ERR_BAD_ARG, "dssm_fc_bwd_dw: null pointer");
     DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_fc_bwd_dw: scale/shift must both be set or both NULL");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_bwd_dw: bad shape");
-    (void)gemm_mode;
     DSSM_REQUIRE(workspace && workspace_bytes >= dssm_fc_bwd_dw_workspace_bytes(R, K, N), DSSM_ERR_WORKSPACE,
                  "dssm_fc_bwd_dw: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int splits = pick_splits(R);
-    const int kps = cdiv(R, splits);
+    int splits = pick_splits(R);
     float* part = (float*)workspace;
-    // C[K,N] = pro(Hprev)^T . dH : M=K (features), reduce over R
-    GemmArgs g{Hprev, dH, part, nullptr, K, N, R, scale, shift, act, B, kps};
-    dim3 grid(cdiv(N, BN), cdiv(K, BM), splits);
-    gemm_f32_kernel<MODE_TN><<<grid, GEMM_THREADS, 0, st>>>(g);
-    LAUNCH_CHECK("fc_bwd_dw");
+    const size_t part_bytes = dssm_fc_bwd_dw_workspace_bytes(R, K, N) - dssm_colsum_workspace_bytes(R, N);
+    if (gemm_mode == DSSM_GEMM_TC_3XTF32) {
+        int rc = dssm_fc_bwd_dw_tc(Hprev, R, K, B, scale, shift, act, dH, N, part, &splits, stream);
+        if (rc != DSSM_OK) return rc;
+    } else {
+        const int kps = cdiv(R, splits);
+        // C[K,N] = pro(Hprev)^T . dH : M=K (features), reduce over R
+        GemmArgs g{Hprev, dH, part, nullptr, K, N, R, scale, shift, act, B, kps};
+        dim3 grid(cdiv(N, BN), cdiv(K, BM), splits);
+        gemm_f32_kernel<MODE_TN><<<grid, GEMM_THREADS, 0, st>>>(g);
+        LAUNCH_CHECK("fc_bwd_dw");
+    }
     const size_t n = (size_t)K * N;
     int rb = cdiv((int64_t)n, 256);
     splitk_reduce_kernel<<<rb, 256, 0, st>>>(part, splits, n, dW);
     LAUNCH_CHECK("fc_bwd_dw_reduce");
     if (db) {
-        char* cs = (char*)workspace + align_up((size_t)splits * K * N * sizeof(float), 256);
+        char* cs = (char*)workspace + part_bytes;
         return dssm_colsum(dH, R, N, db, cs, dssm_colsum_workspace_bytes(R, N), stream);
     }
     return DSSM_OK;

@@ -1,8 +1,459 @@
-// tcgen05 (bf16 operands, fp32 accumulate in TMEM) path of the dense layers -- placeholder entry point.
-// The product refuses the mode loudly until the kernel lands; there is no silent fallback to the fp32 path.
+// Dense-layer contractions on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM)
+// with error-compensated operands ("3xTF32"): every fp32 operand x is split into hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi) and the product is accumulated as a_hi*b_lo + a_lo*b_hi + a_hi*b_hi in fp32.  The
+// dropped a_lo*b_lo term and the rounding of lo are O(2^-22) relative, so this path keeps the 1e-5 parity
+// bar of the fp32 mode while the FFMA work moves to the tensor pipe.
+//
+//   D[M,N] = pro(A)[M,K] . B[N,K]^T (+ bias[n])       A and B both K-major (row-major, K contiguous)
+//
+// pro() is the previous layer's BN scale/shift + activation (new_dssm.py:87,134-136), applied in registers
+// while the A tile is staged, so the normalised tensor never exists in HBM.  Used for
+//   forward   Hout = pro(Hprev) . W        with B = W^T (a [N,K] copy made by transpose_pad_kernel)
+//   backward  dA   = dH . W^T              with B = W itself ([K_layer, N_layer] is K-major for this product)
+//
+// CTA = 256 threads, one 128 x BN output tile, BK = 32 fp32 (one 128-byte swizzle row) per stage, 3 stages.
+// All threads stage operands (global -> registers -> split -> 128B-swizzled smem), thread 0 issues the MMAs,
+// tcgen05.commit releases a stage through an mbarrier, and the 8 warps drain TMEM with tcgen05.ld.
 #include "common.cuh"
 
-extern "C" int dssm_fc_fwd_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t,
-                              const float*, const float*, int32_t, float*, dssm_stream_t) {
-    return dssm::fail(DSSM_ERR_BAD_ARG, "DSSM_GEMM_BF16_TC: tcgen05 dense-layer kernel not built in this revision");
+namespace dssm {
+namespace tc {
+
+constexpr int BM = 128, BK = 32, STAGES = 3, THREADS = 256;
+constexpr int MAX_BN = 160;
+constexpr int TMEM_COLS = 512;
+// The tensor core adds into its fp32 accumulator with truncation, so a long chain of MMAs into ONE accumulator
+// drifts by ~0.5 ulp(acc) per step (measured: 1.5e-5 relative on a 2000-row reduction).  k-blocks therefore go
+// round-robin into NACC accumulators (3 x 160 columns of the 512) that the epilogue adds in registers (RN).
+constexpr int NACC = 3;
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (cute/arch/mma_sm100_desc.hpp
+// SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64))
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// MN-major operand tile (the MN index is the contiguous one in memory).  For 32-bit operands the only MN-major
+// layout the tensor core accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): a 128-byte line holds 32 consecutive MN elements of one k, 4
+// consecutive k lines form the 512-byte swizzle atom in which the 32-byte granule index is XORed with (k & 3)
+// (Swizzle<2,5,2> on byte addresses); the next 32 MN elements are LBO bytes away, the next 4 k are SBO bytes away.
+// Tiles here are laid out [mn_block][k = 0..BK-1][128 B], so SBO = 512 and LBO = BK*128.
+constexpr int MN_LBO = BK * 128;
+constexpr int MN_SBO = 512;
+constexpr int MN_K8_BYTES = 8 * 128;  // one tf32 MMA consumes 8 k lines
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(MN_LBO >> 4) << 16;
+    d |= (uint64_t)(MN_SBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+// InstrDescriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13), a/b_major [15],[16] (0 = K, 1 = MN),
+// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, bool mn_major = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct Args {
+    const float* A;   // [M, K] row-major (lda = K)
+    const float* Bm;  // [N, K] row-major (ldb = ldb)
+    float* D;         // [M, N] row-major
+    const float* bias;
+    const float* scale;
+    const float* shift;  // [2][K] or NULL
+    int M, N, K, ldb, act, Bseg, BN;
+    int k_per_split;  // MN mode: rows of the reduction handled by one blockIdx.z (multiple of BK)
+};
+
+// write one float4 (hi and lo parts) into a swizzled K-major tile: row r, 16-byte chunk c
+__device__ __forceinline__ void stage_chunk(char* tile_hi, char* tile_lo, int r, int c, float4 v) {
+    float4 hi, lo;
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(tile_hi + off) = hi;
+    *reinterpret_cast<float4*>(tile_lo + off) = lo;
+}
+
+// MN-major tile: reduction index kk (0..BK-1), 16-byte chunk c along MN
+__device__ __forceinline__ void stage_chunk_mn(char* tile_hi, char* tile_lo, int kk, int c, float4 v) {
+    float4 hi, lo;
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+    const int off = (c >> 3) * MN_LBO + kk * 128 + (((((c & 7) >> 1) ^ (kk & 3))) << 5) + ((c & 1) << 4);
+    *reinterpret_cast<float4*>(tile_hi + off) = hi;
+    *reinterpret_cast<float4*>(tile_lo + off) = lo;
+}
+
+// MN = false:  D[M,N] = pro(A)[M,K] . B[N,K]^T (+bias)           A, B row-major with K contiguous
+// MN = true :  D[M,N] = sum_r pro(A)[r,M]^T . B[r,N]  over the rows r of this split (A = [R,M], B = [R,N] row-major)
+template <bool MN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
+    extern __shared__ char smem_raw[];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
+    const int BN = g.BN;
+    const int b_tile_bytes = BN * BK * 4;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t idesc = make_idesc_tf32(BM, BN, MN);
+    int kbeg = 0, kend = g.K;
+    if (MN) {
+        kbeg = blockIdx.z * g.k_per_split;
+        kend = min(g.K, kbeg + g.k_per_split);
+    }
+    const int nkb = max(1, (kend - kbeg + BK - 1) / BK);  // at least one (zero-filled) block so the accumulator is defined
+    const int bchunks = BN / 4;                            // 16-byte chunks per B row in MN mode
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES, use = kb / STAGES;
+        char* a_hi = smem + st * stage_bytes;
+        char* a_lo = a_hi + A_TILE_BYTES;
+        char* b_hi = a_lo + A_TILE_BYTES;
+        char* b_lo = b_hi + b_tile_bytes;
+        const int k0 = kbeg + kb * BK;
+        // ---- global -> registers (all loads first) ----
+        float4 av[4], bv[5];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + i * THREADS;
+            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                const int m = m0 + r, k = k0 + c * 4;
+                if (m < g.M && k < g.K) av[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)m * g.K + k));
+            } else {
+                const int kk = id >> 5, c = id & 31;  // 32 reduction rows x 32 chunks of 4 features
+                const int r = k0 + kk, m = m0 + c * 4;
+                if (r < kend && m < g.M) av[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)r * g.M + m));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int id = tid + i * THREADS;
+            bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                const int n = n0 + r, k = k0 + c * 4;
+                if (r < BN && n < g.N && k < g.K) bv[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)n * g.ldb + k));
+            } else {
+                const int kk = id / bchunks, c = id - kk * bchunks;
+                const int r = k0 + kk, n = n0 + c * 4;
+                if (kk < BK && r < kend && n < g.N) bv[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)r * g.N + n));
+            }
+        }
+        // ---- the stage must have been drained by the MMAs that last read it ----
+        if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+        // ---- prologue + split + swizzled store ----
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + i * THREADS;
+            float4 v = av[i];
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                const int m = m0 + r, k = k0 + c * 4;
+                if (m < g.M && k < g.K) {
+                    if (g.scale) {
+                        const int o = (m < g.Bseg ? 0 : g.K) + k;
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + o));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift + o));
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    v.x = act_fwd(v.x, g.act); v.y = act_fwd(v.y, g.act); v.z = act_fwd(v.z, g.act); v.w = act_fwd(v.w, g.act);
+                }
+                stage_chunk(a_hi, a_lo, r, c, v);
+            } else {
+                const int kk = id >> 5, c = id & 31;
+                const int r = k0 + kk, m = m0 + c * 4;
+                if (r < kend && m < g.M) {
+                    if (g.scale) {
+                        const int o = (r < g.Bseg ? 0 : g.M) + m;
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + o));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift + o));
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    v.x = act_fwd(v.x, g.act); v.y = act_fwd(v.y, g.act); v.z = act_fwd(v.z, g.act); v.w = act_fwd(v.w, g.act);
+                }
+                stage_chunk_mn(a_hi, a_lo, kk, c, v);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int id = tid + i * THREADS;
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                if (r < BN) stage_chunk(b_hi, b_lo, r, c, bv[i]);
+            } else {
+                const int kk = id / bchunks, c = id - kk * bchunks;
+                if (kk < BK) stage_chunk_mn(b_hi, b_lo, kk, c, bv[i]);
+            }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t da_hi = MN ? make_desc_mn_sw128(smem_u32(a_hi)) : make_desc_k_sw128(smem_u32(a_hi));
+            const uint64_t da_lo = MN ? make_desc_mn_sw128(smem_u32(a_lo)) : make_desc_k_sw128(smem_u32(a_lo));
+            const uint64_t db_hi = MN ? make_desc_mn_sw128(smem_u32(b_hi)) : make_desc_k_sw128(smem_u32(b_hi));
+            const uint64_t db_lo = MN ? make_desc_mn_sw128(smem_u32(b_lo)) : make_desc_k_sw128(smem_u32(b_lo));
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                // one MMA consumes 8 tf32 along the reduction: 32 B inside the swizzled row (K-major) or eight
+                // 128-byte k lines (MN-major)
+                const uint64_t adv = MN ? (uint64_t)((ks * MN_K8_BYTES) >> 4) : (uint64_t)((ks * 8 * 4) >> 4);
+                const uint32_t acc = tmem_d + (uint32_t)((kb % NACC) * MAX_BN);
+                mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= NACC || ks > 0) ? 1u : 0u);
+                mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+            mma_commit(&empty_bar[st]);             // stage reusable when these MMAs have read it
+            if (kb == nkb - 1) mma_commit(&done_bar);  // accumulator complete
+        }
+    }
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+
+    // ---- epilogue: TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
+    const int lane_grp = warp & 3;
+    const int row = m0 + lane_grp * 32 + lane;
+    const int nchunks = BN / 32;  // BN is a multiple of 32 on this path
+    const int nacc = nkb < NACC ? nkb : NACC;
+    for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;  // +0.0f
+        for (int a = 0; a < nacc; ++a) {
+            uint32_t t[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+                  "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]),
+                  "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]),
+                  "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+        }
+        if (row < g.M) {
+            const int nb = n0 + ch * 32;
+            float* out = g.D + (MN ? (size_t)blockIdx.z * g.M * g.N : 0) + (size_t)row * g.N + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (nb + j + 3 < g.N) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (g.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    *reinterpret_cast<float4*>(out + j) = o;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Wt[n][k] = W[k][n], zero-padded to [Npad][Kpad]   (tiny: <= 300x300)
+__global__ void transpose_pad_kernel(const float* __restrict__ W, int K, int N, float* __restrict__ Wt, int Kpad, int Npad) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int k = k0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int n = n0 + i, k = k0 + threadIdx.x;
+        if (n < Npad && k < Kpad) Wt[(size_t)n * Kpad + k] = tile[threadIdx.x][i];
+    }
+}
+
+static int pick_bn(int N) {
+    // N tiles of equal width, multiple of 32 (epilogue chunks), at most MAX_BN
+    const int tiles = (N + MAX_BN - 1) / MAX_BN;
+    int bn = ((N + tiles - 1) / tiles + 31) / 32 * 32;
+    return bn > MAX_BN ? MAX_BN : bn;
+}
+
+static size_t smem_bytes(int BN) { return (size_t)STAGES * (2 * A_TILE_BYTES + 2 * (size_t)BN * BK * 4) + 1024; }
+
+static int launch(const Args& a, cudaStream_t st, int splits = 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        attr_set = true;
+    }
+    if (splits > 0) {
+        dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM), splits);
+        gemm_tc3_kernel<true><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
+    } else {
+        dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
+        gemm_tc3_kernel<false><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
+    }
+    LAUNCH_CHECK("gemm_tc3");
+    return DSSM_OK;
+}
+
+// number of reduction splits for the dW contraction: fill the chip, keep >= 4 k-blocks per split
+static int pick_splits_tc(int R, int tiles) {
+    int s = (sm_count() + tiles - 1) / tiles;
+    const int max_s = (R + 4 * BK - 1) / (4 * BK);
+    if (s > max_s) s = max_s;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : s;
+}
+
+}  // namespace tc
+}  // namespace dssm
+
+using namespace dssm;
+
+extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N) {
+    if (K <= 0 || N <= 0) return 0;
+    const size_t kpad = (size_t)(K + 31) / 32 * 32, npad = (size_t)(N + 31) / 32 * 32;
+    return align_up(kpad * npad * sizeof(float), 256);
+}
+
+// forward on the tensor cores: needs a [Npad, Kpad] transposed copy of W in `workspace`
+extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                              int32_t act, const float* W, const float* bias, int32_t N, float* Hout, void* workspace,
+                              size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
+    DSSM_REQUIRE(aligned16(Hprev) && aligned16(W) && aligned16(Hout) && (!bias || aligned16(bias)) && (!scale || (aligned16(scale) && aligned16(shift))),
+                 DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
+    DSSM_REQUIRE(workspace && workspace_bytes >= dssm_fc_tc_workspace_bytes(K, N), DSSM_ERR_WORKSPACE, "dssm_fc_fwd (tc): workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kpad = (K + 31) / 32 * 32, npad = (N + 31) / 32 * 32;
+    float* Wt = (float*)workspace;
+    dim3 tg(cdiv(npad, 32), cdiv(kpad, 32)), tb(32, 8);
+    tc::transpose_pad_kernel<<<tg, tb, 0, st>>>(W, K, N, Wt, kpad, npad);
+    LAUNCH_CHECK("transpose_pad");
+    tc::Args a{Hprev, Wt, Hout, bias, scale, shift, R, N, K, kpad, act, B, tc::pick_bn(N), 0};
+    return tc::launch(a, st);
+}
+
+// dA[R,K] = dH[R,N] . W[K,N]^T on the tensor cores: both operands are K-major as they lie in memory
+extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
+                                 dssm_stream_t stream) {
+    DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
+    DSSM_REQUIRE(aligned16(dH) && aligned16(W) && aligned16(dA), DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
+    // D[M=R, N'=K] = A[M=R, K'=N] . B[N'=K, K'=N]^T
+    tc::Args a{dH, W, dA, nullptr, nullptr, nullptr, R, K, N, N, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0};
+    return tc::launch(a, (cudaStream_t)stream);
+}
+
+// dW[K,N] partials = pro(Hprev)[rows of split]^T . dH[rows of split] on the tensor cores (both operands MN-major
+// as they lie in memory); `partials` receives [splits][K][N]; returns the split count through *splits_out.
+extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_t N) {
+    if (R <= 0 || K <= 0 || N <= 0) return 0;
+    const int tiles = cdiv(N, tc::pick_bn(N)) * cdiv(K, tc::BM);
+    return align_up((size_t)tc::pick_splits_tc(R, tiles) * K * N * sizeof(float), 256);
+}
+
+extern "C" int dssm_fc_bwd_dw_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                                 int32_t act, const float* dH, int32_t N, float* partials, int32_t* splits_out,
+                                 dssm_stream_t stream) {
+    DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
+    DSSM_REQUIRE(aligned16(Hprev) && aligned16(dH) && aligned16(partials) && (!scale || (aligned16(scale) && aligned16(shift))),
+                 DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
+    const int bn = tc::pick_bn(N);
+    const int tiles = cdiv(N, bn) * cdiv(K, tc::BM);
+    const int splits = tc::pick_splits_tc(R, tiles);
+    int kps = cdiv(R, splits);
+    kps = (kps + tc::BK - 1) / tc::BK * tc::BK;
+    // D[M=K_layer, N] ; reduction over the R rows
+    tc::Args a{Hprev, dH, partials, nullptr, scale, shift, K, N, R, 0, act, B, bn, kps};
+    *splits_out = splits;
+    return tc::launch(a, (cudaStream_t)stream, splits);
 }

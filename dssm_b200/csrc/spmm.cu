@@ -171,7 +171,7 @@ spmm_bwd_scatter_scalar_kernel(const int* __restrict__ indptr, const int* __rest
 // backward, method 0: per-batch CSC (device-built) + gather-by-column.
 //
 //  csc_hist     colcnt[c] += 1 for every non-zero                       (int atomics, exact)
-//  csc_scan     colptr = exclusive_scan(colcnt); itemptr = exclusive_scan(max(1, ceil(cnt/CSC_CHUNK)))
+//  csc_scan_*   colptr = exclusive_scan(colcnt); itemptr = exclusive_scan(max(1, ceil(cnt/CSC_CHUNK)))
 //  csc_fill     (row, value) of every non-zero into its column segment  (slot by atomic cursor)
 //  dw_gather    one warp per item (<= CSC_CHUNK entries of one column): sum value * dH[row,:];
 //               single-item columns write their dW1 row directly; multi-item columns park partial sums
@@ -186,44 +186,82 @@ __global__ void csc_hist_kernel(const int* __restrict__ indptr, const int* __res
         atomicAdd(colcnt + __ldg(indices + p), 1);
 }
 
-// single block; every thread scans a contiguous slice, block-level scan of the slice totals in smem
-__global__ void __launch_bounds__(1024)
-csc_scan_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ colptr, int* __restrict__ cursor,
-                int* __restrict__ itemptr) {
-    __shared__ int s_cnt[1024];
-    __shared__ int s_itm[1024];
-    const int t = threadIdx.x;
-    const int per = (D + blockDim.x - 1) / blockDim.x;
-    const int lo = min(D, t * per), hi = min(D, lo + per);
-    int a = 0, b = 0;
-    for (int c = lo; c < hi; ++c) {
-        const int n = colcnt[c];
-        a += n;
-        b += max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK);
+// Two-pass multi-block exclusive scan of (colcnt, items-per-column) over the D columns.
+//   pass A: every block scans SCAN_TILE consecutive columns (coalesced 4-per-thread loads, shuffle scans) and
+//           writes block-local exclusive prefixes plus its two block totals;
+//   pass B: every block adds the sum of the preceding blocks' totals and emits colptr / cursor / itemptr.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ int items_of(int n) { return max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK); }
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+csc_scan_local_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ colptr, int* __restrict__ itemptr,
+                      int2* __restrict__ block_totals) {
+    __shared__ int2 warp_tot[SCAN_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int base = blockIdx.x * SCAN_TILE + t * SCAN_PER_THREAD;
+    int c[SCAN_PER_THREAD], it[SCAN_PER_THREAD];
+    int sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        const int col = base + i;
+        c[i] = col < D ? colcnt[col] : 0;
+        it[i] = col < D ? items_of(c[i]) : 0;
+        sa += c[i];
+        sb += it[i];
     }
-    s_cnt[t] = a;
-    s_itm[t] = b;
+    // inclusive warp scan of the per-thread sums
+    int xa = sa, xb = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ya; xb += yb; }
+    }
+    if (lane == 31) warp_tot[w] = make_int2(xa, xb);
     __syncthreads();
-    // Hillis-Steele inclusive scan over blockDim.x totals
-    for (int off = 1; off < blockDim.x; off <<= 1) {
-        int xa = 0, xb = 0;
-        if (t >= off) { xa = s_cnt[t - off]; xb = s_itm[t - off]; }
-        __syncthreads();
-        if (t >= off) { s_cnt[t] += xa; s_itm[t] += xb; }
-        __syncthreads();
+    int wa = 0, wb = 0;
+    for (int i = 0; i < w; ++i) { wa += warp_tot[i].x; wb += warp_tot[i].y; }
+    int ra = wa + xa - sa, rb = wb + xb - sb;  // exclusive prefix of this thread inside the block
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        const int col = base + i;
+        if (col < D) { colptr[col] = ra; itemptr[col] = rb; }
+        ra += c[i];
+        rb += it[i];
     }
-    int ra = s_cnt[t] - a, rb = s_itm[t] - b;  // exclusive prefix of this slice
-    for (int c = lo; c < hi; ++c) {
-        const int n = colcnt[c];
-        colptr[c] = ra;
-        cursor[c] = ra;
-        itemptr[c] = rb;
-        ra += n;
-        rb += max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK);
+    if (t == SCAN_THREADS - 1) block_totals[blockIdx.x] = make_int2(ra, rb);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, int* __restrict__ colptr,
+                    int* __restrict__ cursor, int* __restrict__ itemptr) {
+    __shared__ int2 red[SCAN_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int oa = 0, ob = 0;
+    for (int b = t; b < (int)blockIdx.x; b += SCAN_THREADS) { oa += block_totals[b].x; ob += block_totals[b].y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { oa += __shfl_xor_sync(0xffffffffu, oa, o); ob += __shfl_xor_sync(0xffffffffu, ob, o); }
+    if (lane == 0) red[w] = make_int2(oa, ob);
+    __syncthreads();
+    oa = 0; ob = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) { oa += red[i].x; ob += red[i].y; }
+    const int base = blockIdx.x * SCAN_TILE + t * SCAN_PER_THREAD;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        const int col = base + i;
+        if (col < D) {
+            const int p = colptr[col] + oa;
+            colptr[col] = p;
+            cursor[col] = p;
+            itemptr[col] += ob;
+        }
     }
-    if (t == blockDim.x - 1) {
-        colptr[D] = s_cnt[t];
-        itemptr[D] = s_itm[t];
+    if ((int)blockIdx.x == n_blocks - 1 && t == 0) {
+        colptr[D] = oa + block_totals[n_blocks - 1].x;
+        itemptr[D] = ob + block_totals[n_blocks - 1].y;
     }
 }
 
@@ -313,6 +351,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
 
 struct CscWorkspace {
     int *colcnt, *done, *colptr, *cursor, *itemptr, *csc_row;
+    int2* block_totals;
     float* csc_val;
     float* partial;
     size_t bytes;
@@ -326,6 +365,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
     w.itemptr = a.take<int>(D + 1);
+    w.block_totals = a.take<int2>((size_t)(D + SCAN_TILE - 1) / SCAN_TILE + 1);
     w.csc_row = a.take<int>((size_t)max_nnz);
     w.csc_val = a.take<float>((size_t)max_nnz);
     const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
@@ -448,8 +488,11 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
     const int nsm = sm_count();
     csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
     LAUNCH_CHECK("csc_hist");
-    csc_scan_kernel<<<1, 1024, 0, st>>>(w.colcnt, D, w.colptr, w.cursor, w.itemptr);
-    LAUNCH_CHECK("csc_scan");
+    const int scan_blocks = cdiv(D, SCAN_TILE);
+    csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
+    LAUNCH_CHECK("csc_scan_local");
+    csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr);
+    LAUNCH_CHECK("csc_scan_add");
     {
         const int wpb = SPMM_THREADS / 32;
         int blocks = cdiv(R, wpb);

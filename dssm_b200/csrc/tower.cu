@@ -58,8 +58,8 @@ struct dssm_tower {
     float *bn_mean[DSSM_MAX_LAYERS + 1], *bn_var[DSSM_MAX_LAYERS + 1], *bn_rstd[DSSM_MAX_LAYERS + 1],
         *bn_scale[DSSM_MAX_LAYERS + 1], *bn_shift[DSSM_MAX_LAYERS + 1];
     float *Y, *qnorm, *dnorm, *cos_raw, *cos_sim, *prob, *loss_terms, *loss;
-    void *bn_ws, *dw_ws, *sp_ws;
-    size_t bn_ws_bytes, dw_ws_bytes, sp_ws_bytes;
+    void *bn_ws, *dw_ws, *sp_ws, *fc_ws;
+    size_t bn_ws_bytes, dw_ws_bytes, sp_ws_bytes, fc_ws_bytes;
     // last forward's CSR (backward reuses it)
     const int32_t *cur_indptr, *cur_indices;
     const float* cur_values;
@@ -137,6 +137,13 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     }
     t->dw_ws_bytes = dw;
     t->dw_ws = a.take<char>(dw);
+    size_t fcw = 0;
+    for (int l = 2; l <= n; ++l) {
+        const size_t x = dssm_fc_fwd_workspace_bytes(t->L[l - 1], t->L[l], t->cfg.gemm_mode);
+        fcw = x > fcw ? x : fcw;
+    }
+    t->fc_ws_bytes = fcw;
+    t->fc_ws = a.take<char>(fcw ? fcw : 256);
     t->sp_ws_bytes = dssm_spmm_bwd_dw_workspace_bytes(R, t->D, t->L[1], max_nnz);
     t->sp_ws = a.take<char>(t->sp_ws_bytes);
     return a.off;
@@ -147,7 +154,7 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     DSSM_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= DSSM_MAX_LAYERS, DSSM_ERR_BAD_ARG, "dssm_tower_create: n_layers=%d out of [1,%d]", cfg->n_layers, DSSM_MAX_LAYERS);
     DSSM_REQUIRE(cfg->TRIGRAM_D > 0 && cfg->NEG > 0 && cfg->query_BS > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: TRIGRAM_D, NEG, query_BS must be positive");
     DSSM_REQUIRE(cfg->act == DSSM_ACT_RELU || cfg->act == DSSM_ACT_TANH || cfg->act == DSSM_ACT_NONE, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown act %d", cfg->act);
-    DSSM_REQUIRE(cfg->gemm_mode == DSSM_GEMM_FP32 || cfg->gemm_mode == DSSM_GEMM_BF16_TC, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown gemm_mode %d", cfg->gemm_mode);
+    DSSM_REQUIRE(cfg->gemm_mode == DSSM_GEMM_FP32 || cfg->gemm_mode == DSSM_GEMM_TC_3XTF32, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown gemm_mode %d", cfg->gemm_mode);
     for (int l = 0; l < cfg->n_layers; ++l)
         DSSM_REQUIRE(cfg->layers[l] > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: layer %d width %d", l + 1, cfg->layers[l]);
     const int64_t rows = (int64_t)(2 + cfg->NEG) * cfg->query_BS;
@@ -284,7 +291,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         if (l < n) {
             const std::string ns = std::to_string(l + 1);
             TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
-                            t->h[l + 1], c.gemm_mode, s));
+                            t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));
         } else {
             TRY(dssm_bn_act_apply(t->h[l], R, t->L[l], B, sc, sh, c.act, t->Y, s));
         }

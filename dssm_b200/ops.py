@@ -110,8 +110,9 @@ def fc_fwd(Hprev, W, bias, scale=None, shift=None, act=None, B: int = 0, gemm_mo
     R, K = Hprev.shape
     N = W.shape[1]
     out = _f32((R, N), Hprev.device)
+    ws = _ws(lib.dssm_fc_fwd_workspace_bytes(K, N, GEMM[gemm_mode]), Hprev.device)
     check(lib.dssm_fc_fwd(ptr(Hprev), R, K, B, ptr(scale), ptr(shift), ACT[act], ptr(W), ptr(bias), N, ptr(out),
-                          GEMM[gemm_mode], stream_ptr()))
+                          GEMM[gemm_mode], ptr(ws), ws.numel(), stream_ptr()))
     return out
 
 

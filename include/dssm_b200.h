@@ -52,9 +52,10 @@ enum {
 enum { DSSM_ACT_NONE = 0, DSSM_ACT_RELU = 1, DSSM_ACT_TANH = 2 };
 
 /* Arithmetic of the dense-layer contractions (FC2.. and their gradients).
- *   FP32   : FFMA, fp32 accumulate -- the 1e-5 parity mode.
- *   BF16_TC: tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate in TMEM) -- stated tolerance. */
-enum { DSSM_GEMM_FP32 = 0, DSSM_GEMM_BF16_TC = 1 };
+ *   FP32      : FFMA, fp32 accumulate.
+ *   TC_3XTF32 : tcgen05.mma kind::tf32 with error-compensated operands (x = hi + lo, three MMAs per product,
+ *               fp32 accumulate in TMEM): tensor-core path that keeps the 1e-5 parity bar. */
+enum { DSSM_GEMM_FP32 = 0, DSSM_GEMM_TC_3XTF32 = 1 };
 
 #define DSSM_MAX_LAYERS 8
 
@@ -137,9 +138,10 @@ int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_
  *   Hout[R,N] = act(Hprev*scale + shift)[R,K] . W[K,N] + bias[N]
  * scale/shift are [2][K] (per segment) or NULL (identity); act applies also when scale is NULL.
  */
+size_t dssm_fc_fwd_workspace_bytes(int32_t K, int32_t N, int32_t gemm_mode); /* 0 for DSSM_GEMM_FP32 */
 int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                 int32_t act, const float* W, const float* bias, int32_t N, float* Hout, int32_t gemm_mode,
-                dssm_stream_t stream);
+                void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 /* dA[R,K] = dH[R,N] . W[K,N]^T   (gradient w.r.t. the post-activation input of the layer) */
 int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
                    int32_t gemm_mode, dssm_stream_t stream);

@@ -215,6 +215,36 @@ def test_fc_fwd_bwd(R, K, N, B, with_bn):
     assert_close(ops.colsum(dev(dH)).cpu().numpy(), dH.astype(np.float64).sum(0), TOL, "colsum")
 
 
+@pytest.mark.parametrize("R,K,N,B", [(600, 300, 300, 100), (6144, 300, 128, 1024), (130, 64, 68, 130), (257, 300, 300, 100),
+                                      (49152, 300, 300, 8192)])
+@pytest.mark.parametrize("with_bn", [True, False])
+def test_fc_tensor_core_3xtf32(R, K, N, B, with_bn):
+    """tcgen05 kind::tf32 with error-compensated operands (3 MMAs per product): same 1e-5 bar as the FFMA path."""
+    from dssm_b200 import ops
+
+    rng = np.random.default_rng(R + K + N)
+    h = rng.standard_normal((R, K)).astype(np.float32)
+    W = rng.uniform(-0.1, 0.1, (K, N)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (N,)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, (2, K)).astype(np.float32) if with_bn else None
+    shift = rng.uniform(-0.5, 0.5, (2, K)).astype(np.float32) if with_bn else None
+    a = h.astype(np.float64)
+    if with_bn:
+        a = np.concatenate([a[:B] * scale[0] + shift[0], a[B:] * scale[1] + shift[1]])
+    a = np.maximum(a, 0)
+    want = a @ W.astype(np.float64) + b
+    got = ops.fc_fwd(dev(h), dev(W), dev(b), dev(scale) if with_bn else None, dev(shift) if with_bn else None, "relu", B,
+                     gemm_mode="tc_3xtf32")
+    assert_close(got.cpu().numpy(), want, TOL, "fc_fwd tc")
+    dH = rng.standard_normal((R, N)).astype(np.float32)
+    dA = ops.fc_bwd_dx(dev(dH), dev(W), gemm_mode="tc_3xtf32").cpu().numpy()
+    assert_close(dA, dH.astype(np.float64) @ W.T.astype(np.float64), TOL, "fc_bwd_dx tc")
+    dW, db = ops.fc_bwd_dw(dev(h), dev(dH), dev(scale) if with_bn else None, dev(shift) if with_bn else None, "relu", B,
+                           gemm_mode="tc_3xtf32")
+    assert_close(dW.cpu().numpy(), a.T @ dH.astype(np.float64), TOL, "fc_bwd_dw tc")
+    assert_close(db.cpu().numpy(), dH.astype(np.float64).sum(0), TOL, "db tc")
+
+
 def test_add_layer_reference_call_shape():
     """add_layer(inputs, in_size, out_size, activation_function) creates Xavier-uniform W and b (dssm_v3.py:44-53)."""
     from dssm_b200 import add_layer

@@ -123,11 +123,13 @@ def test_tower_against_golden(name):
         assert_close(v, orc.ema[k], FWD_TOL, f"ema {k} (no Adam)")
 
 
-def test_golden_one_step_details():
+@pytest.mark.parametrize("gemm_mode", ["fp32", "tc_3xtf32"])
+def test_golden_one_step_details(gemm_mode):
     from dssm_b200 import DSSMTower
 
     for name in GOLDEN_CASES:
         conf, Xs, params, _ = load_golden(name)
+        conf.gemm_mode = gemm_mode
         t = DSSMTower(conf, max_nnz=Xs[0].nnz + 8, params=params)
         one_step_checks(conf, t, Xs[0], params)
 
@@ -142,12 +144,13 @@ CONFIGS = {
 }
 
 
+@pytest.mark.parametrize("gemm_mode", ["fp32", "tc_3xtf32"])
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_tower_against_live_oracle(name):
+def test_tower_against_live_oracle(name, gemm_mode):
     from dssm_b200 import Config, DSSMTower
     from dssm_b200.synthetic import init_params, lambdas_for, make_batch
 
-    conf = Config(**CONFIGS[name])
+    conf = Config(gemm_mode=gemm_mode, **CONFIGS[name])
     lq, ld = lambdas_for(conf)
     vm = "tfidf" if name == "C4_small_nobn" else "count"
     batches = [make_batch(conf, seed=s, lam_query=lq, lam_doc=ld, value_mode=vm) for s in range(2)]
@@ -158,7 +161,7 @@ def test_tower_against_live_oracle(name):
     lo = orc.train_step(batches[1].to_scipy())
     lg = t.train_step(t.to_device(batches[1])).item()
     assert abs(lg - lo) <= 2e-4 * abs(lo)
-    assert_update_close(t.export_params(), orc.p, params, conf.use_bn, "after 2 steps", l2_tol=2e-2)
+    assert_update_close(t.export_params(), orc.p, params, conf.use_bn, "after 2 steps", l2_tol=5e-2)
     for k, v in t.export_ema().items():
         if k.endswith("ema_var"):
             assert_close(v, orc.ema[k], 2e-3, f"ema {k}")
