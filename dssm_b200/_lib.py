@@ -74,7 +74,7 @@ SIGNATURES = {
     "dssm_bn_act_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_fc_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dssm_fc_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
-    "dssm_fc_bwd_dx": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p]),
+    "dssm_fc_bwd_dx": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
     "dssm_fc_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dssm_fc_bwd_dw": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _p, _i32, _p, _sz, _p]),
     "dssm_colsum_workspace_bytes": (_sz, [_i32, _i32]),

@@ -8,33 +8,43 @@
 
 namespace dssm {
 
-constexpr int BN_CHUNK_ROWS = 256;  // rows per partial
+constexpr int BN_CHUNK_ROWS = 256;  // minimum rows per partial (workspace sizing uses this)
+constexpr int BN_MAX_CHUNKS = 32;   // per segment: keeps the serial merge in the finalize kernels short
 constexpr int BN_TX = 32;           // columns per block
 constexpr int BN_TY = 8;            // row lanes per block
 
 // chunk table: chunks never straddle the segment boundary
-__host__ __device__ inline int bn_chunks_of(int rows) { return (rows + BN_CHUNK_ROWS - 1) / BN_CHUNK_ROWS; }
+__host__ __device__ inline int bn_chunks_of(int rows, int chunk_rows = BN_CHUNK_ROWS) { return (rows + chunk_rows - 1) / chunk_rows; }
+// rows per chunk for a batch: >= BN_CHUNK_ROWS and at most BN_MAX_CHUNKS chunks in the larger segment
+static inline int bn_chunk_rows(int R, int B) {
+    const int seg = B > R - B ? B : R - B;
+    int cr = (seg + BN_MAX_CHUNKS - 1) / BN_MAX_CHUNKS;
+    cr = (cr + 7) / 8 * 8;
+    return cr < BN_CHUNK_ROWS ? BN_CHUNK_ROWS : cr;
+}
 
 // partial layout: [3][n_chunks_total][L]  (count as float, mean, M2)
 __global__ void __launch_bounds__(BN_TX * BN_TY)
-bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total) {
+bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
     __shared__ float red[BN_TY][BN_TX + 1];
     __shared__ float s_mean[BN_TX];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
-    const int nq = bn_chunks_of(B);
+    const int nq = bn_chunks_of(B, chunk_rows);
     int chunk = blockIdx.y, r0, r1;
     if (chunk < nq) {
-        r0 = chunk * BN_CHUNK_ROWS;
-        r1 = min(B, r0 + BN_CHUNK_ROWS);
+        r0 = chunk * chunk_rows;
+        r1 = min(B, r0 + chunk_rows);
     } else {
-        r0 = B + (chunk - nq) * BN_CHUNK_ROWS;
-        r1 = min(R, r0 + BN_CHUNK_ROWS);
+        r0 = B + (chunk - nq) * chunk_rows;
+        r1 = min(R, r0 + chunk_rows);
     }
     const int n = r1 - r0;
     float s = 0.f;
-    if (col < L)
+    if (col < L) {
+#pragma unroll 8
         for (int r = r0 + ty; r < r1; r += BN_TY) s += __ldg(X + (size_t)r * L + col);
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0) {
@@ -46,11 +56,13 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
     __syncthreads();
     const float mu = s_mean[tx];
     float q = 0.f;
-    if (col < L)
+    if (col < L) {
+#pragma unroll 8
         for (int r = r0 + ty; r < r1; r += BN_TY) {
             const float d = __ldg(X + (size_t)r * L + col) - mu;
             q = fmaf(d, d, q);
         }
+    }
     __syncthreads();
     red[ty][tx] = q;
     __syncthreads();
@@ -64,14 +76,15 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
     }
 }
 
-// one thread per (segment, column): merge chunk partials in order, EMA, scale/shift
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L,
-                                   int on_train, int update_ema, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ ema_mean,
-                                   float* __restrict__ ema_var, float eps, float decay, float* __restrict__ mean_o,
-                                   float* __restrict__ var_o, float* __restrict__ rstd_o, float* __restrict__ scale_o,
-                                   float* __restrict__ shift_o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (segment, column): lane c holds chunk c's (n, mean, M2) -- at most BN_MAX_CHUNKS = 32 chunks per
+// segment by construction -- merged by a fixed shuffle tree with Chan's formula; lane 0 writes EMA, scale/shift
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, int on_train, int update_ema,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ema_mean,
+                   float* __restrict__ ema_var, float eps, float decay, float* __restrict__ mean_o, float* __restrict__ var_o,
+                   float* __restrict__ rstd_o, float* __restrict__ scale_o, float* __restrict__ shift_o) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= 2 * L) return;
     const int seg = i / L, col = i - seg * L;
     float mean, var;
@@ -80,16 +93,26 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int n_chunks_
         const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
         if (c0 == c1) return;  // empty segment (single-instance call, B == R)
         float n = 0.f, mu = 0.f, m2 = 0.f;
-        for (int c = c0; c < c1; ++c) {
-            const float nb = part[((size_t)0 * n_chunks_total + c) * L + col];
-            const float mb = part[((size_t)1 * n_chunks_total + c) * L + col];
-            const float qb = part[((size_t)2 * n_chunks_total + c) * L + col];
-            const float nt = n + nb;
-            const float delta = mb - mu;
-            mu = mu + delta * (nb / nt);
-            m2 = m2 + qb + delta * delta * (n * nb / nt);
-            n = nt;
+        if (c0 + lane < c1) {
+            const int c = c0 + lane;
+            n = part[((size_t)0 * n_chunks_total + c) * L + col];
+            mu = part[((size_t)1 * n_chunks_total + c) * L + col];
+            m2 = part[((size_t)2 * n_chunks_total + c) * L + col];
         }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // lane l absorbs lane l+o: chunks stay merged in ascending order
+            const float nb = __shfl_down_sync(0xffffffffu, n, o);
+            const float mb = __shfl_down_sync(0xffffffffu, mu, o);
+            const float qb = __shfl_down_sync(0xffffffffu, m2, o);
+            const float nt = n + nb;
+            if (nb > 0.f && (lane & (2 * o - 1)) == 0) {
+                const float delta = mb - mu;
+                mu = mu + delta * (nb / nt);
+                m2 = m2 + qb + delta * delta * (n * nb / nt);
+                n = nt;
+            }
+        }
+        if (lane != 0) return;
         mean = mu;
         var = m2 / n;  // biased (tf.nn.moments)
         if (update_ema) {
@@ -99,6 +122,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int n_chunks_
             ema_var[i] = ev - (1.f - decay) * (ev - var);
         }
     } else {
+        if (lane != 0) return;
         mean = ema_mean[i];
         var = ema_var[i];
     }
@@ -111,17 +135,26 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int n_chunks_
     shift_o[i] = beta[i] - mean * sc;
 }
 
-__global__ void bn_act_apply_kernel(const float* __restrict__ X, int R, int L, int B, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int act, float* __restrict__ Y) {
-    const size_t total = (size_t)R * L;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / L), c = (int)(i - (size_t)r * L);
-        float x = __ldg(X + i);
-        if (scale) {
-            const int o = (r < B ? 0 : L) + c;
-            x = fmaf(x, __ldg(scale + o), __ldg(shift + o));
+constexpr int EW_ROWS = 4;  // rows per block iteration of the elementwise kernels
+
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const float* __restrict__ X, int R, int L, int B, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, float* __restrict__ Y) {
+    for (int r0 = blockIdx.x * EW_ROWS; r0 < R; r0 += gridDim.x * EW_ROWS) {
+        for (int c = threadIdx.x; c < L; c += blockDim.x) {
+#pragma unroll
+            for (int j = 0; j < EW_ROWS; ++j) {
+                const int r = r0 + j;
+                if (r < R) {
+                    float x = __ldg(X + (size_t)r * L + c);
+                    if (scale) {
+                        const int o = (r < B ? 0 : L) + c;
+                        x = fmaf(x, __ldg(scale + o), __ldg(shift + o));
+                    }
+                    Y[(size_t)r * L + c] = act_fwd(x, act);
+                }
+            }
         }
-        Y[i] = act_fwd(x, act);
     }
 }
 
@@ -130,22 +163,23 @@ __global__ void bn_act_apply_kernel(const float* __restrict__ X, int R, int L, i
 __global__ void __launch_bounds__(BN_TX * BN_TY)
 bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
-                     const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total) {
+                     const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
     __shared__ float red0[BN_TY][BN_TX + 1];
     __shared__ float red1[BN_TY][BN_TX + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
-    const int nq = bn_chunks_of(B);
+    const int nq = bn_chunks_of(B, chunk_rows);
     int chunk = blockIdx.y, r0, r1, seg;
     if (chunk < nq) {
-        seg = 0; r0 = chunk * BN_CHUNK_ROWS; r1 = min(B, r0 + BN_CHUNK_ROWS);
+        seg = 0; r0 = chunk * chunk_rows; r1 = min(B, r0 + chunk_rows);
     } else {
-        seg = 1; r0 = B + (chunk - nq) * BN_CHUNK_ROWS; r1 = min(R, r0 + BN_CHUNK_ROWS);
+        seg = 1; r0 = B + (chunk - nq) * chunk_rows; r1 = min(R, r0 + chunk_rows);
     }
     float sg = 0.f, sgx = 0.f;
     if (col < L) {
         const int o = seg * L + col;
         const float mu = __ldg(mean + o), rs = __ldg(rstd + o), sc = __ldg(scale + o), sh = __ldg(shift + o);
+#pragma unroll 4
         for (int r = r0 + ty; r < r1; r += BN_TY) {
             const float h = __ldg(H + (size_t)r * L + col);
             const float a = act_fwd(fmaf(h, sc, sh), act);
@@ -166,40 +200,57 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= 2 * L) return;
     const int seg = i / L, col = i - seg * L;
     const int c0 = seg == 0 ? 0 : nq_chunks;
     const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
     float b = 0.f, g = 0.f;
-    for (int c = c0; c < c1; ++c) {
+    for (int c = c0 + lane; c < c1; c += 32) {
         b += part[((size_t)0 * n_chunks_total + c) * L + col];
         g += part[((size_t)1 * n_chunks_total + c) * L + col];
     }
-    dbeta[i] = b;
-    dgamma[i] = g;
+    b = warp_sum(b);
+    g = warp_sum(g);
+    if (lane == 0) {
+        dbeta[i] = b;
+        dgamma[i] = g;
+    }
 }
 
 // pass 2 (in place): dH = gamma*rstd * (g - dbeta/n - xhat*dgamma/n)
-__global__ void bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
-                                    const float* __restrict__ gamma, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta) {
-    const size_t total = (size_t)R * L;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / L), c = (int)(i - (size_t)r * L);
-        const int seg = r < B ? 0 : 1;
-        const int o = seg * L + c;
-        const float n = seg == 0 ? (float)B : (float)(R - B);
-        const float h = __ldg(H + i);
-        const float a = act_fwd(fmaf(h, __ldg(scale + o), __ldg(shift + o)), act);
-        const float g = dA[i] * act_grad_from_out(a, act);
-        const float rs = __ldg(rstd + o);
-        const float xhat = (h - __ldg(mean + o)) * rs;
-        dA[i] = (__ldg(gamma + o) * rs) * (g - __ldg(dbeta + o) / n - xhat * (__ldg(dgamma + o) / n));
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
+                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ dgamma,
+                    const float* __restrict__ dbeta) {
+    for (int r0 = blockIdx.x * EW_ROWS; r0 < R; r0 += gridDim.x * EW_ROWS) {
+        for (int c = threadIdx.x; c < L; c += blockDim.x) {
+            float h[EW_ROWS], d[EW_ROWS];
+#pragma unroll
+            for (int j = 0; j < EW_ROWS; ++j) {
+                const int r = r0 + j;
+                h[j] = r < R ? __ldg(H + (size_t)r * L + c) : 0.f;
+                d[j] = r < R ? dA[(size_t)r * L + c] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < EW_ROWS; ++j) {
+                const int r = r0 + j;
+                if (r >= R) continue;
+                const int seg = r < B ? 0 : 1;
+                const int o = seg * L + c;
+                const float n = seg == 0 ? (float)B : (float)(R - B);
+                const float a = act_fwd(fmaf(h[j], __ldg(scale + o), __ldg(shift + o)), act);
+                const float g = d[j] * act_grad_from_out(a, act);
+                const float rs = __ldg(rstd + o);
+                const float xhat = (h[j] - __ldg(mean + o)) * rs;
+                dA[(size_t)r * L + c] = (__ldg(gamma + o) * rs) * (g - __ldg(dbeta + o) / n - xhat * (__ldg(dgamma + o) / n));
+            }
+        }
     }
 }
 
@@ -209,6 +260,12 @@ __global__ void act_bwd_kernel(float* __restrict__ dA, const float* __restrict__
         const float a = act_fwd(__ldg(H + i), act);
         dA[i] = dA[i] * act_grad_from_out(a, act);
     }
+}
+
+static int row_blocks(int R) {
+    int b = (R + EW_ROWS - 1) / EW_ROWS;
+    const int cap = sm_count() * 16;
+    return b < cap ? (b ? b : 1) : cap;
 }
 
 static int ew_blocks(size_t total) {
@@ -236,16 +293,17 @@ extern "C" int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, 
                  "dssm_bn_forward: null pointer");
     DSSM_REQUIRE(R > 0 && L > 0 && B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_forward: need 0 < B <= R (R=%d B=%d)", R, B);
     cudaStream_t st = (cudaStream_t)stream;
-    const int nq = bn_chunks_of(B), nd = bn_chunks_of(R - B), nt = nq + nd;
+    const int cr = bn_chunk_rows(R, B);
+    const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
     float* part = (float*)workspace;
     if (on_train) {
         DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
                      "dssm_bn_forward: workspace too small");
         dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
-        bn_stats_kernel<<<grid, block, 0, st>>>(X, R, L, B, part, nt);
+        bn_stats_kernel<<<grid, block, 0, st>>>(X, R, L, B, part, nt, cr);
         LAUNCH_CHECK("bn_stats");
     }
-    bn_finalize_kernel<<<cdiv(2 * L, 128), 128, 0, st>>>(part, nt, nq, L, on_train, update_ema, gamma, beta, ema_mean,
+    bn_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, on_train, update_ema, gamma, beta, ema_mean,
                                                          ema_var, eps, ema_decay, mean, var, rstd, scale, shift);
     LAUNCH_CHECK("bn_finalize");
     return DSSM_OK;
@@ -257,7 +315,7 @@ extern "C" int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B
     DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_bn_act_apply: scale/shift must both be set or both NULL");
     DSSM_REQUIRE(R >= 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_apply: bad shape");
     if (R == 0) return DSSM_OK;
-    bn_act_apply_kernel<<<ew_blocks((size_t)R * L), 256, 0, (cudaStream_t)stream>>>(X, R, L, B, scale, shift, act, Y);
+    bn_act_apply_kernel<<<row_blocks(R), 256, 0, (cudaStream_t)stream>>>(X, R, L, B, scale, shift, act, Y);
     LAUNCH_CHECK("bn_act_apply");
     return DSSM_OK;
 }
@@ -276,16 +334,17 @@ extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_
     }
     DSSM_REQUIRE(gamma && mean && rstd && shift && dgamma && dbeta, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null BN pointer");
     DSSM_REQUIRE(B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
-    const int nq = bn_chunks_of(B), nd = bn_chunks_of(R - B), nt = nq + nd;
+    const int cr = bn_chunk_rows(R, B);
+    const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
     DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)2 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
                  "dssm_bn_act_backward: workspace too small");
     float* part = (float*)workspace;
     dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
-    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt);
+    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr);
     LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<cdiv(2 * L, 128), 128, 0, st>>>(part, nt, nq, L, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, dgamma, dbeta);
     LAUNCH_CHECK("bn_bwd_finalize");
-    bn_bwd_apply_kernel<<<ew_blocks((size_t)R * L), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift,
+    bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift,
                                                                  dgamma, dbeta);
     LAUNCH_CHECK("bn_bwd_apply");
     return DSSM_OK;

@@ -198,7 +198,7 @@ using namespace dssm;
 extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N);
 extern "C" int dssm_fc_fwd_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t,
                               const float*, const float*, int32_t, float*, void*, size_t, dssm_stream_t);
-extern "C" int dssm_fc_bwd_dx_tc(const float*, int32_t, int32_t, const float*, int32_t, float*, dssm_stream_t);
+extern "C" int dssm_fc_bwd_dx_tc(const float*, int32_t, int32_t, const float*, int32_t, float*, void*, size_t, dssm_stream_t);
 extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_t N);
 extern "C" int dssm_fc_bwd_dw_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t, const float*,
                                  int32_t, float*, int32_t*, dssm_stream_t);
@@ -224,10 +224,10 @@ extern "C" int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, 
 }
 
 extern "C" int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
-                              int32_t gemm_mode, dssm_stream_t stream) {
+                              int32_t gemm_mode, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(dH && W && dA, DSSM_ERR_BAD_ARG, "dssm_fc_bwd_dx: null pointer");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_bwd_dx: bad shape");
-    if (gemm_mode == DSSM_GEMM_TC_3XTF32) return dssm_fc_bwd_dx_tc(dH, R, N, W, K, dA, stream);
+    if (gemm_mode == DSSM_GEMM_TC_3XTF32) return dssm_fc_bwd_dx_tc(dH, R, N, W, K, dA, workspace, workspace_bytes, stream);
     // C[R,K] = dH[R,N] . W[K,N]^T : reduce over N
     GemmArgs g{dH, W, dA, nullptr, R, K, N, nullptr, nullptr, DSSM_ACT_NONE, 0, 0};
     dim3 grid(cdiv(K, BN), cdiv(R, BM), 1);

@@ -8,8 +8,11 @@
 //
 // pro() is the previous layer's BN scale/shift + activation (new_dssm.py:87,134-136), applied in registers
 // while the A tile is staged, so the normalised tensor never exists in HBM.  Used for
-//   forward   Hout = pro(Hprev) . W        with B = W^T (a [N,K] copy made by transpose_pad_kernel)
-//   backward  dA   = dH . W^T              with B = W itself ([K_layer, N_layer] is K-major for this product)
+//   forward   Hout = pro(Hprev) . W        with B = W^T
+//   backward  dA   = dH . W^T              with B = W ([K_layer, N_layer] is K-major for this product)
+// In both, B is the (small) weight matrix: it is split and swizzled ONCE per call into a tile image
+// (make_b_image_kernel) that each CTA pulls into shared memory with cp.async.bulk + mbarrier complete_tx, so the
+// threads only stage the activation operand.
 //
 // CTA = 256 threads, one 128 x BN output tile, BK = 32 fp32 (one 128-byte swizzle row) per stage, 3 stages.
 // All threads stage operands (global -> registers -> split -> 128B-swizzled smem), thread 0 issues the MMAs,
@@ -103,6 +106,14 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// bulk async copy global -> shared (async proxy), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -118,6 +129,7 @@ struct Args {
     const float* shift;  // [2][K] or NULL
     int M, N, K, ldb, act, Bseg, BN;
     int k_per_split;  // MN mode: rows of the reduction handled by one blockIdx.z (multiple of BK)
+    const char* Bimg;  // K-major mode: pre-split, pre-swizzled image of B (make_b_image_kernel); NULL = stage B in registers
 };
 
 // write one float4 (hi and lo parts) into a swizzled K-major tile: row r, 16-byte chunk c
@@ -146,6 +158,7 @@ template <bool MN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     extern __shared__ char smem_raw[];
     __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t full_bar[STAGES];  // B tile landed (bulk async copy), K-major mode with a B image
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_base_slot;
 
@@ -162,7 +175,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);
+        }
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,95 +194,108 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     }
     const int nkb = max(1, (kend - kbeg + BK - 1) / BK);  // at least one (zero-filled) block so the accumulator is defined
     const int bchunks = BN / 4;                            // 16-byte chunks per B row in MN mode
+    const bool use_img = g.Bimg != nullptr;
+    // image layout: [n_tile][k_block][hi | lo][BN rows x 128 B, SW128]
+    const char* b_img = use_img ? g.Bimg + (size_t)blockIdx.x * nkb * 2 * b_tile_bytes : nullptr;
 
-    for (int kb = 0; kb < nkb; ++kb) {
+    // ---- operand staging, software-pipelined one k-block ahead in registers --------------------------------
+    struct Regs {
+        float4 a[4], b[5], sc[4], sh[4];
+    };
+    auto load_regs = [&](int kb, Regs& q) {
+        const int k0 = kbeg + kb * BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + i * THREADS;
+            q.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q.sc[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            q.sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                const int m = m0 + r, k = k0 + c * 4;
+                if (m < g.M && k < g.K) {
+                    q.a[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)m * g.K + k));
+                    if (g.scale) {
+                        const int o = (m < g.Bseg ? 0 : g.K) + k;
+                        q.sc[i] = __ldg(reinterpret_cast<const float4*>(g.scale + o));
+                        q.sh[i] = __ldg(reinterpret_cast<const float4*>(g.shift + o));
+                    }
+                }
+            } else {
+                const int kk = id >> 5, c = id & 31;  // 32 reduction rows x 32 chunks of 4 features
+                const int r = k0 + kk, m = m0 + c * 4;
+                if (r < kend && m < g.M) {
+                    q.a[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)r * g.M + m));
+                    if (g.scale) {
+                        const int o = (r < g.Bseg ? 0 : g.M) + m;
+                        q.sc[i] = __ldg(reinterpret_cast<const float4*>(g.scale + o));
+                        q.sh[i] = __ldg(reinterpret_cast<const float4*>(g.shift + o));
+                    }
+                }
+            }
+        }
+        if (!MN && use_img) return;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int id = tid + i * THREADS;
+            q.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!MN) {
+                const int r = id >> 3, c = id & 7;
+                const int n = n0 + r, k = k0 + c * 4;
+                if (r < BN && n < g.N && k < g.K) q.b[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)n * g.ldb + k));
+            } else {
+                const int kk = id / bchunks, c = id - kk * bchunks;
+                const int r = k0 + kk, n = n0 + c * 4;
+                if (kk < BK && r < kend && n < g.N) q.b[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)r * g.N + n));
+            }
+        }
+    };
+    auto process = [&](int kb, const Regs& q) {
         const int st = kb % STAGES, use = kb / STAGES;
         char* a_hi = smem + st * stage_bytes;
         char* a_lo = a_hi + A_TILE_BYTES;
         char* b_hi = a_lo + A_TILE_BYTES;
         char* b_lo = b_hi + b_tile_bytes;
         const int k0 = kbeg + kb * BK;
-        // ---- global -> registers (all loads first) ----
-        float4 av[4], bv[5];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int id = tid + i * THREADS;
-            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!MN) {
-                const int r = id >> 3, c = id & 7;
-                const int m = m0 + r, k = k0 + c * 4;
-                if (m < g.M && k < g.K) av[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)m * g.K + k));
-            } else {
-                const int kk = id >> 5, c = id & 31;  // 32 reduction rows x 32 chunks of 4 features
-                const int r = k0 + kk, m = m0 + c * 4;
-                if (r < kend && m < g.M) av[i] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)r * g.M + m));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int id = tid + i * THREADS;
-            bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!MN) {
-                const int r = id >> 3, c = id & 7;
-                const int n = n0 + r, k = k0 + c * 4;
-                if (r < BN && n < g.N && k < g.K) bv[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)n * g.ldb + k));
-            } else {
-                const int kk = id / bchunks, c = id - kk * bchunks;
-                const int r = k0 + kk, n = n0 + c * 4;
-                if (kk < BK && r < kend && n < g.N) bv[i] = __ldg(reinterpret_cast<const float4*>(g.Bm + (size_t)r * g.N + n));
-            }
-        }
-        // ---- the stage must have been drained by the MMAs that last read it ----
+        // the stage must have been drained by the MMAs that last read it
         if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
-        // ---- prologue + split + swizzled store ----
+        // prologue (BN scale/shift + activation) + hi/lo split + swizzled store
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int id = tid + i * THREADS;
-            float4 v = av[i];
+            float4 v = q.a[i];
+            bool valid;
             if (!MN) {
-                const int r = id >> 3, c = id & 7;
-                const int m = m0 + r, k = k0 + c * 4;
-                if (m < g.M && k < g.K) {
-                    if (g.scale) {
-                        const int o = (m < g.Bseg ? 0 : g.K) + k;
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + o));
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift + o));
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                    v.x = act_fwd(v.x, g.act); v.y = act_fwd(v.y, g.act); v.z = act_fwd(v.z, g.act); v.w = act_fwd(v.w, g.act);
-                }
-                stage_chunk(a_hi, a_lo, r, c, v);
+                valid = (m0 + (id >> 3) < g.M) && (k0 + (id & 7) * 4 < g.K);
             } else {
-                const int kk = id >> 5, c = id & 31;
-                const int r = k0 + kk, m = m0 + c * 4;
-                if (r < kend && m < g.M) {
-                    if (g.scale) {
-                        const int o = (r < g.Bseg ? 0 : g.M) + m;
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + o));
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift + o));
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                    v.x = act_fwd(v.x, g.act); v.y = act_fwd(v.y, g.act); v.z = act_fwd(v.z, g.act); v.w = act_fwd(v.w, g.act);
-                }
-                stage_chunk_mn(a_hi, a_lo, kk, c, v);
+                valid = (k0 + (id >> 5) < kend) && (m0 + (id & 31) * 4 < g.M);
             }
+            if (valid) {  // padding stays exactly zero (act(shift) must not leak into it)
+                v.x = act_fwd(fmaf(v.x, q.sc[i].x, q.sh[i].x), g.act);
+                v.y = act_fwd(fmaf(v.y, q.sc[i].y, q.sh[i].y), g.act);
+                v.z = act_fwd(fmaf(v.z, q.sc[i].z, q.sh[i].z), g.act);
+                v.w = act_fwd(fmaf(v.w, q.sc[i].w, q.sh[i].w), g.act);
+            }
+            if (!MN) stage_chunk(a_hi, a_lo, id >> 3, id & 7, v);
+            else stage_chunk_mn(a_hi, a_lo, id >> 5, id & 31, v);
         }
+        if (MN || !use_img) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int id = tid + i * THREADS;
-            if (!MN) {
-                const int r = id >> 3, c = id & 7;
-                if (r < BN) stage_chunk(b_hi, b_lo, r, c, bv[i]);
-            } else {
-                const int kk = id / bchunks, c = id - kk * bchunks;
-                if (kk < BK) stage_chunk_mn(b_hi, b_lo, kk, c, bv[i]);
+            for (int i = 0; i < 5; ++i) {
+                const int id = tid + i * THREADS;
+                if (!MN) {
+                    const int r = id >> 3, c = id & 7;
+                    if (r < BN) stage_chunk(b_hi, b_lo, r, c, q.b[i]);
+                } else {
+                    const int kk = id / bchunks, c = id - kk * bchunks;
+                    if (kk < BK) stage_chunk_mn(b_hi, b_lo, kk, c, q.b[i]);
+                }
             }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
+            if (!MN && use_img) mbar_wait(&full_bar[st], (uint32_t)(use & 1));  // this block's B tile has landed
             tc_fence_after();
             const uint64_t da_hi = MN ? make_desc_mn_sw128(smem_u32(a_hi)) : make_desc_k_sw128(smem_u32(a_hi));
             const uint64_t da_lo = MN ? make_desc_mn_sw128(smem_u32(a_lo)) : make_desc_k_sw128(smem_u32(a_lo));
@@ -282,8 +311,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
                 mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
                 mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
             }
-            mma_commit(&empty_bar[st]);             // stage reusable when these MMAs have read it
-            if (kb == nkb - 1) mma_commit(&done_bar);  // accumulator complete
+            mma_commit(&empty_bar[st]);                // stage reusable when these MMAs have read it
+            if (kb == nkb - 1) mma_commit(&done_bar);  // accumulators complete
+            if (!MN && use_img && kb + 2 < nkb) {      // prefetch the B tile two k-blocks ahead
+                const int st2 = (kb + 2) % STAGES, use2 = (kb + 2) / STAGES;
+                if (use2 > 0) mbar_wait(&empty_bar[st2], (uint32_t)((use2 - 1) & 1));
+                bulk_copy_g2s(smem + st2 * stage_bytes + 2 * A_TILE_BYTES, b_img + (size_t)(kb + 2) * 2 * b_tile_bytes,
+                              (uint32_t)(2 * b_tile_bytes), &full_bar[st2]);
+            }
+        }
+    };
+
+    if (!MN && use_img && tid == 0) {
+        for (int kb = 0; kb < 2 && kb < nkb; ++kb)
+            bulk_copy_g2s(smem + kb * stage_bytes + 2 * A_TILE_BYTES, b_img + (size_t)kb * 2 * b_tile_bytes,
+                          (uint32_t)(2 * b_tile_bytes), &full_bar[kb]);
+    }
+    Regs r0, r1;
+    load_regs(0, r0);
+    for (int kb = 0; kb < nkb; kb += 2) {
+        if (kb + 1 < nkb) load_regs(kb + 1, r1);  // in flight while block kb is transformed, stored and issued
+        process(kb, r0);
+        if (kb + 1 < nkb) {
+            if (kb + 2 < nkb) load_regs(kb + 2, r0);
+            process(kb + 1, r1);
         }
     }
     mbar_wait(&done_bar, 0);
@@ -343,18 +394,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     }
 }
 
-// Wt[n][k] = W[k][n], zero-padded to [Npad][Kpad]   (tiny: <= 300x300)
-__global__ void transpose_pad_kernel(const float* __restrict__ W, int K, int N, float* __restrict__ Wt, int Kpad, int Npad) {
-    __shared__ float tile[32][33];
-    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int k = k0 + i, n = n0 + threadIdx.x;
-        tile[i][threadIdx.x] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int n = n0 + i, k = k0 + threadIdx.x;
-        if (n < Npad && k < Kpad) Wt[(size_t)n * Kpad + k] = tile[threadIdx.x][i];
+// Pre-split, pre-swizzled image of the weight operand B[n][k] for the K-major kernel, built once per call
+// (<= 820 KB): [n_tile][k_block][hi | lo][BN rows x 128 B].  transposed: B[n][k] = src[k*ld + n], else src[n*ld + k].
+__global__ void __launch_bounds__(256)
+make_b_image_kernel(const float* __restrict__ src, int N, int K, int ld, int transposed, int BN, int nkb, char* __restrict__ img) {
+    const int nt = blockIdx.x, kb = blockIdx.y;
+    const int b_tile_bytes = BN * BK * 4;
+    char* hi = img + ((size_t)nt * nkb + kb) * 2 * b_tile_bytes;
+    char* lo = hi + b_tile_bytes;
+    for (int id = threadIdx.x; id < BN * 8; id += blockDim.x) {
+        const int r = id >> 3, c = id & 7;
+        const int n = nt * BN + r, k = kb * BK + c * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = 0.f;
+            if (n < N && k + j < K) v[j] = transposed ? __ldg(src + (size_t)(k + j) * ld + n) : __ldg(src + (size_t)n * ld + k + j);
+        }
+        stage_chunk(hi, lo, r, c, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -399,38 +456,55 @@ static int pick_splits_tc(int R, int tiles) {
 
 using namespace dssm;
 
-extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N) {
-    if (K <= 0 || N <= 0) return 0;
-    const size_t kpad = (size_t)(K + 31) / 32 * 32, npad = (size_t)(N + 31) / 32 * 32;
-    return align_up(kpad * npad * sizeof(float), 256);
+// image of an operand with N rows (tiled by BN) and K reduction columns
+static size_t image_bytes(int N, int K) {
+    const int bn = tc::pick_bn(N);
+    return align_up((size_t)cdiv(N, bn) * cdiv(K, tc::BK) * 2 * bn * tc::BK * 4, 256);
 }
 
-// forward on the tensor cores: needs a [Npad, Kpad] transposed copy of W in `workspace`
+extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N) {
+    if (K <= 0 || N <= 0) return 0;
+    const size_t f = image_bytes(N, K), b = image_bytes(K, N);  // forward (B = W^T) and dX (B = W)
+    return f > b ? f : b;
+}
+
+static int build_image(const float* src, int N, int K, int ld, int transposed, char* img, cudaStream_t st) {
+    const int bn = tc::pick_bn(N), nkb = cdiv(K, tc::BK);
+    dim3 grid(cdiv(N, bn), nkb);
+    tc::make_b_image_kernel<<<grid, 256, 0, st>>>(src, N, K, ld, transposed, bn, nkb, img);
+    LAUNCH_CHECK("make_b_image");
+    return DSSM_OK;
+}
+
+// forward on the tensor cores: B = W^T as a pre-split swizzled image in `workspace`
 extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                               int32_t act, const float* W, const float* bias, int32_t N, float* Hout, void* workspace,
                               size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(Hprev) && aligned16(W) && aligned16(Hout) && (!bias || aligned16(bias)) && (!scale || (aligned16(scale) && aligned16(shift))),
                  DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
-    DSSM_REQUIRE(workspace && workspace_bytes >= dssm_fc_tc_workspace_bytes(K, N), DSSM_ERR_WORKSPACE, "dssm_fc_fwd (tc): workspace too small");
+    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
+                 "dssm_fc_fwd (tc): workspace too small or unaligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int kpad = (K + 31) / 32 * 32, npad = (N + 31) / 32 * 32;
-    float* Wt = (float*)workspace;
-    dim3 tg(cdiv(npad, 32), cdiv(kpad, 32)), tb(32, 8);
-    tc::transpose_pad_kernel<<<tg, tb, 0, st>>>(W, K, N, Wt, kpad, npad);
-    LAUNCH_CHECK("transpose_pad");
-    tc::Args a{Hprev, Wt, Hout, bias, scale, shift, R, N, K, kpad, act, B, tc::pick_bn(N), 0};
+    int rc = build_image(W, N, K, N, 1, (char*)workspace, st);  // B[n][k] = W[k][n]
+    if (rc != DSSM_OK) return rc;
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)workspace};
     return tc::launch(a, st);
 }
 
-// dA[R,K] = dH[R,N] . W[K,N]^T on the tensor cores: both operands are K-major as they lie in memory
-extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
-                                 dssm_stream_t stream) {
+// dA[R,K] = dH[R,N] . W[K,N]^T on the tensor cores: B = W (rows = K_layer, reduction = N_layer) as an image
+extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA, void* workspace,
+                                 size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(dH) && aligned16(W) && aligned16(dA), DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
+    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(K, N) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
+                 "dssm_fc_bwd_dx (tc): workspace too small or unaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = build_image(W, K, N, N, 0, (char*)workspace, st);  // B[n'=k_layer][k'=n_layer] = W[k_layer][n_layer]
+    if (rc != DSSM_OK) return rc;
     // D[M=R, N'=K] = A[M=R, K'=N] . B[N'=K, K'=N]^T
-    tc::Args a{dH, W, dA, nullptr, nullptr, nullptr, R, K, N, N, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0};
-    return tc::launch(a, (cudaStream_t)stream);
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)workspace};
+    return tc::launch(a, st);
 }
 
 // dW[K,N] partials = pro(Hprev)[rows of split]^T . dH[rows of split] on the tensor cores (both operands MN-major
@@ -453,7 +527,7 @@ extern "C" int dssm_fc_bwd_dw_tc(const float* Hprev, int32_t R, int32_t K, int32
     int kps = cdiv(R, splits);
     kps = (kps + tc::BK - 1) / tc::BK * tc::BK;
     // D[M=K_layer, N] ; reduction over the R rows
-    tc::Args a{Hprev, dH, partials, nullptr, scale, shift, K, N, R, 0, act, B, bn, kps};
+    tc::Args a{Hprev, dH, partials, nullptr, scale, shift, K, N, R, 0, act, B, bn, kps, nullptr};
     *splits_out = splits;
     return tc::launch(a, (cudaStream_t)stream, splits);
 }

@@ -236,7 +236,8 @@ csc_scan_local_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ c
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, int* __restrict__ colptr,
-                    int* __restrict__ cursor, int* __restrict__ itemptr) {
+                    int* __restrict__ cursor, int* __restrict__ itemptr, const int* __restrict__ colcnt,
+                    int* __restrict__ item_col) {
     __shared__ int2 red[SCAN_THREADS / 32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     int oa = 0, ob = 0;
@@ -256,7 +257,10 @@ csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, 
             const int p = colptr[col] + oa;
             colptr[col] = p;
             cursor[col] = p;
-            itemptr[col] += ob;
+            const int first = itemptr[col] + ob;
+            itemptr[col] = first;
+            const int ni = items_of(colcnt[col]);  // item -> column map, so the gather needs no search
+            for (int i = 0; i < ni; ++i) item_col[first + i] = col;
         }
     }
     if ((int)blockIdx.x == n_blocks - 1 && t == 0) {
@@ -283,7 +287,8 @@ csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 
 template <int NCH>
 __global__ void __launch_bounds__(SPMM_THREADS)
-dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ csc_row,
+dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ item_col,
+                    const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
                     float4* __restrict__ partial4, int* __restrict__ done, int D, int L4) {
     const int lane = threadIdx.x & 31;
@@ -291,13 +296,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
     const int stride = gridDim.x * wpb;
     const int n_items = __ldg(itemptr + D);
     for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += stride) {
-        // column of this item: last c with itemptr[c] <= item
-        int lo = 0, hi = D;  // invariant: itemptr[lo] <= item < itemptr[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(itemptr + mid) <= item) lo = mid; else hi = mid;
-        }
-        const int c = lo;
+        const int c = __ldg(item_col + item);
         const int first_item = __ldg(itemptr + c);
         const int n_col_items = __ldg(itemptr + c + 1) - first_item;
         const int cs = __ldg(colptr + c), ce = __ldg(colptr + c + 1);
@@ -328,6 +327,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                 __threadfence();
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
                 for (int i = 0; i < n_col_items; ++i) {
 #pragma unroll
                     for (int k = 0; k < NCH; ++k) {
@@ -352,6 +352,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
 struct CscWorkspace {
     int *colcnt, *done, *colptr, *cursor, *itemptr, *csc_row;
     int2* block_totals;
+    int* item_col;
     float* csc_val;
     float* partial;
     size_t bytes;
@@ -369,6 +370,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.csc_row = a.take<int>((size_t)max_nnz);
     w.csc_val = a.take<float>((size_t)max_nnz);
     const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
+    w.item_col = a.take<int>(max_items);
     w.partial = a.take<float>(max_items * (size_t)L1);
     w.bytes = a.off;
     return w;
@@ -377,7 +379,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
 template <int NCH>
 static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, cudaStream_t st) {
     const int blocks = sm_count() * 8;
-    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(w.colptr, w.itemptr, w.csc_row, w.csc_val,
+    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(w.colptr, w.itemptr, w.item_col, w.csc_row, w.csc_val,
                                                             (const float4*)dH, (float4*)dW, (float4*)w.partial,
                                                             w.done, D, L1 / 4);
 }
@@ -491,7 +493,8 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
     const int scan_blocks = cdiv(D, SCAN_TILE);
     csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
     LAUNCH_CHECK("csc_scan_local");
-    csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr);
+    csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr,
+                                                              w.colcnt, w.item_col);
     LAUNCH_CHECK("csc_scan_add");
     {
         const int wpb = SPMM_THREADS / 32;

@@ -323,7 +323,8 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s) {
             const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
             TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
                                t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
-            TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, s));
+            TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, t->fc_ws,
+                               t->fc_ws_bytes, s));
         } else {
             mark(PH_DENSE_BWD);
             if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];

@@ -120,7 +120,8 @@ def fc_bwd_dx(dH, W, gemm_mode: str = "fp32"):
     R, N = dH.shape
     K = W.shape[0]
     dA = _f32((R, K), dH.device)
-    check(lib.dssm_fc_bwd_dx(ptr(dH), R, N, ptr(W), K, ptr(dA), GEMM[gemm_mode], stream_ptr()))
+    ws = _ws(lib.dssm_fc_fwd_workspace_bytes(K, N, GEMM[gemm_mode]), dH.device)
+    check(lib.dssm_fc_bwd_dx(ptr(dH), R, N, ptr(W), K, ptr(dA), GEMM[gemm_mode], ptr(ws), ws.numel(), stream_ptr()))
     return dA
 
 

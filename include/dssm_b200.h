@@ -138,13 +138,14 @@ int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_
  *   Hout[R,N] = act(Hprev*scale + shift)[R,K] . W[K,N] + bias[N]
  * scale/shift are [2][K] (per segment) or NULL (identity); act applies also when scale is NULL.
  */
-size_t dssm_fc_fwd_workspace_bytes(int32_t K, int32_t N, int32_t gemm_mode); /* 0 for DSSM_GEMM_FP32 */
+/* workspace of dssm_fc_fwd and dssm_fc_bwd_dx (the pre-split weight image of the tensor-core path); 0 for FP32 */
+size_t dssm_fc_fwd_workspace_bytes(int32_t K, int32_t N, int32_t gemm_mode);
 int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                 int32_t act, const float* W, const float* bias, int32_t N, float* Hout, int32_t gemm_mode,
                 void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 /* dA[R,K] = dH[R,N] . W[K,N]^T   (gradient w.r.t. the post-activation input of the layer) */
 int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA,
-                   int32_t gemm_mode, dssm_stream_t stream);
+                   int32_t gemm_mode, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 /* dW[K,N] = act(Hprev*scale+shift)^T . dH ;  db[N] = column sums of dH.  Deterministic split-K. */
 size_t dssm_fc_bwd_dw_workspace_bytes(int32_t R, int32_t K, int32_t N);
 int dssm_fc_bwd_dw(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
