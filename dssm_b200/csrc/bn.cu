@@ -1,9 +1,9 @@
 // batch_normalization (new_dssm.py:62-88) for the two instances of one layer (query rows [0,B), doc rows
 // [B,R)), its EMA update, the fused normalise+activation, and the backward through act(BN(x)).
 //
-// Moments are computed two-pass per row chunk (chunk mean, then centred sum of squares) and the chunk
-// triples (n, mean, M2) are merged in chunk order with Chan's formula -- no E[x^2]-E[x]^2 cancellation, and
-// the result does not depend on the launch geometry.  Reductions across rows use warp shuffles.
+// Moments are computed per row chunk from shifted data (pivot = the chunk's first row) and the chunk triples
+// (n, mean, M2) are merged by a fixed shuffle tree with Chan's formula -- no E[x^2]-E[x]^2 cancellation, and the
+// result is deterministic.
 #include "common.cuh"
 
 namespace dssm {
@@ -12,6 +12,7 @@ constexpr int BN_CHUNK_ROWS = 256;  // minimum rows per partial (workspace sizin
 constexpr int BN_MAX_CHUNKS = 32;   // per segment: keeps the serial merge in the finalize kernels short
 constexpr int BN_TX = 32;           // columns per block
 constexpr int BN_TY = 8;            // row lanes per block
+constexpr int MLP = 8;              // independent row loads in flight per thread in the column reductions
 
 // chunk table: chunks never straddle the segment boundary
 __host__ __device__ inline int bn_chunks_of(int rows, int chunk_rows = BN_CHUNK_ROWS) { return (rows + chunk_rows - 1) / chunk_rows; }
@@ -27,7 +28,6 @@ static inline int bn_chunk_rows(int R, int B) {
 __global__ void __launch_bounds__(BN_TX * BN_TY)
 bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
     __shared__ float red[BN_TY][BN_TX + 1];
-    __shared__ float s_mean[BN_TX];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
     const int nq = bn_chunks_of(B, chunk_rows);
@@ -40,39 +40,43 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
         r1 = min(R, r0 + chunk_rows);
     }
     const int n = r1 - r0;
-    float s = 0.f;
+    // single pass over the chunk with shifted data: d = x - K, K = the chunk's first row (a sample, so |mean-K| is
+    // O(sigma) and  M2 = sum d^2 - (sum d)^2/n  loses at most a digit -- unlike E[x^2]-E[x]^2 around zero)
+    float s = 0.f, q = 0.f;
+    float K = 0.f;
     if (col < L) {
-#pragma unroll 8
-        for (int r = r0 + ty; r < r1; r += BN_TY) s += __ldg(X + (size_t)r * L + col);
-    }
-    red[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0) {
-        float t = 0.f;
+        K = __ldg(X + (size_t)r0 * L + col);
+        int r = r0 + ty;
+        for (; r + (MLP - 1) * BN_TY < r1; r += MLP * BN_TY) {  // MLP independent loads in flight per thread
+            float v[MLP];
 #pragma unroll
-        for (int i = 0; i < BN_TY; ++i) t += red[i][tx];
-        s_mean[tx] = t / (float)n;
-    }
-    __syncthreads();
-    const float mu = s_mean[tx];
-    float q = 0.f;
-    if (col < L) {
-#pragma unroll 8
-        for (int r = r0 + ty; r < r1; r += BN_TY) {
-            const float d = __ldg(X + (size_t)r * L + col) - mu;
+            for (int u = 0; u < MLP; ++u) v[u] = __ldg(X + (size_t)(r + u * BN_TY) * L + col);
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                const float d = v[u] - K;
+                s += d;
+                q = fmaf(d, d, q);
+            }
+        }
+#pragma unroll 1
+        for (; r < r1; r += BN_TY) {
+            const float d = __ldg(X + (size_t)r * L + col) - K;
+            s += d;
             q = fmaf(d, d, q);
         }
     }
-    __syncthreads();
-    red[ty][tx] = q;
+    __shared__ float red2[BN_TY][BN_TX + 1];
+    red[ty][tx] = s;
+    red2[ty][tx] = q;
     __syncthreads();
     if (ty == 0 && col < L) {
-        float t = 0.f;
+        float ts = 0.f, tq = 0.f;
 #pragma unroll
-        for (int i = 0; i < BN_TY; ++i) t += red[i][tx];
+        for (int i = 0; i < BN_TY; ++i) { ts += red[i][tx]; tq += red2[i][tx]; }
+        const float md = ts / (float)n;
         part[((size_t)0 * n_chunks_total + chunk) * L + col] = (float)n;
-        part[((size_t)1 * n_chunks_total + chunk) * L + col] = mu;
-        part[((size_t)2 * n_chunks_total + chunk) * L + col] = t;
+        part[((size_t)1 * n_chunks_total + chunk) * L + col] = K + md;
+        part[((size_t)2 * n_chunks_total + chunk) * L + col] = fmaxf(tq - ts * md, 0.f);
     }
 }
 
@@ -179,8 +183,23 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
     if (col < L) {
         const int o = seg * L + col;
         const float mu = __ldg(mean + o), rs = __ldg(rstd + o), sc = __ldg(scale + o), sh = __ldg(shift + o);
-#pragma unroll 4
-        for (int r = r0 + ty; r < r1; r += BN_TY) {
+        int r = r0 + ty;
+        for (; r + (MLP - 1) * BN_TY < r1; r += MLP * BN_TY) {
+            float hv[MLP], dv[MLP];
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                hv[u] = __ldg(H + (size_t)(r + u * BN_TY) * L + col);
+                dv[u] = __ldg(dA + (size_t)(r + u * BN_TY) * L + col);
+            }
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                const float a = act_fwd(fmaf(hv[u], sc, sh), act);
+                const float g = dv[u] * act_grad_from_out(a, act);
+                sg += g;
+                sgx = fmaf(g, (hv[u] - mu) * rs, sgx);
+            }
+        }
+        for (; r < r1; r += BN_TY) {
             const float h = __ldg(H + (size_t)r * L + col);
             const float a = act_fwd(fmaf(h, sc, sh), act);
             const float g = __ldg(dA + (size_t)r * L + col) * act_grad_from_out(a, act);

@@ -170,8 +170,17 @@ colsum_partial_kernel(const float* __restrict__ X, int R, int N, float* __restri
     const int col = blockIdx.x * 32 + tx;
     const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
     float s = 0.f;
-    if (col < N)
-        for (int r = r0 + ty; r < r1; r += 8) s += __ldg(X + (size_t)r * N + col);
+    if (col < N) {
+        int r = r0 + ty;
+        for (; r + 7 * 8 < r1; r += 64) {  // 8 independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(X + (size_t)(r + u * 8) * N + col);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; r < r1; r += 8) s += __ldg(X + (size_t)r * N + col);
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && col < N) {

@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
         kend = min(g.K, kbeg + g.k_per_split);
     }
     const int nkb = max(1, (kend - kbeg + BK - 1) / BK);  // at least one (zero-filled) block so the accumulator is defined
+    // short reductions (K <= 384: the forward and dX contractions) stay well inside the 1e-5 bar with one
+    // accumulator (120 chained MMAs); only long ones (dW over thousands of rows) need the rotation
+    const int nacc_used = nkb <= 12 ? 1 : NACC;
     const int bchunks = BN / 4;                            // 16-byte chunks per B row in MN mode
     const bool use_img = g.Bimg != nullptr;
     // image layout: [n_tile][k_block][hi | lo][BN rows x 128 B, SW128]
@@ -306,8 +309,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
                 // one MMA consumes 8 tf32 along the reduction: 32 B inside the swizzled row (K-major) or eight
                 // 128-byte k lines (MN-major)
                 const uint64_t adv = MN ? (uint64_t)((ks * MN_K8_BYTES) >> 4) : (uint64_t)((ks * 8 * 4) >> 4);
-                const uint32_t acc = tmem_d + (uint32_t)((kb % NACC) * MAX_BN);
-                mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= NACC || ks > 0) ? 1u : 0u);
+                const uint32_t acc = tmem_d + (uint32_t)((kb % nacc_used) * MAX_BN);
+                mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= nacc_used || ks > 0) ? 1u : 0u);
                 mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
                 mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
             }
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     const int lane_grp = warp & 3;
     const int row = m0 + lane_grp * 32 + lane;
     const int nchunks = BN / 32;  // BN is a multiple of 32 on this path
-    const int nacc = nkb < NACC ? nkb : NACC;
+    const int nacc = nkb < nacc_used ? nkb : nacc_used;
     for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
         uint32_t r[32];
 #pragma unroll

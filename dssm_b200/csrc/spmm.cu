@@ -59,6 +59,63 @@ __device__ __forceinline__ void gather_accumulate(const int* __restrict__ idx, c
     }
 }
 
+// Same contract as gather_accumulate, but the gathered rows travel global -> shared with cp.async (LDGSTS): no
+// registers are tied up by loads in flight, so every warp keeps RING rows (RING*NCH*512 B) outstanding instead of
+// GATHER_UNROLL.  A lane reads back only the chunks it copied itself, so cp.async.wait_group is the only sync needed.
+constexpr int RING = 4;
+template <int NCH>
+__device__ __forceinline__ void gather_accumulate_async(const int* __restrict__ idx, const float* __restrict__ val, int s,
+                                                        int e, const float4* __restrict__ src4, int L4, int lane,
+                                                        float4* ring /* this warp's [RING][NCH*32] */, float4 (&acc)[NCH]) {
+    auto issue = [&](int slot, int c) {
+        const float4* rowp = src4 + (size_t)c * L4;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            if (col < L4) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + slot * (NCH * 32) + col);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowp + col) : "memory");
+            }
+        }
+    };
+    for (int base = s; base < e; base += 32) {
+        const int n = min(32, e - base);
+        int my_c = 0;
+        float my_v = 0.f;
+        if (lane < n) {
+            my_c = __ldg(idx + base + lane);
+            my_v = __ldg(val + base + lane);
+        }
+#pragma unroll
+        for (int t = 0; t < RING; ++t) {  // prologue: RING rows in flight (empty groups keep the count uniform)
+            const int c = __shfl_sync(0xffffffffu, my_c, t);
+            if (t < n) issue(t, c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int t = 0; t < n; ++t) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+            const float v = __shfl_sync(0xffffffffu, my_v, t);
+            const int slot = t % RING;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int col = lane + 32 * k;
+                if (col < L4) {
+                    const float4 w = ring[slot * (NCH * 32) + col];
+                    acc[k].x = fmaf(v, w.x, acc[k].x);
+                    acc[k].y = fmaf(v, w.y, acc[k].y);
+                    acc[k].z = fmaf(v, w.z, acc[k].z);
+                    acc[k].w = fmaf(v, w.w, acc[k].w);
+                }
+            }
+            const int tn = t + RING;
+            const int c = __shfl_sync(0xffffffffu, my_c, tn & 31);
+            if (tn < n) issue(slot, c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(SPMM_THREADS)
 spmm_fwd_v4_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ values,
@@ -290,12 +347,21 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ item_col,
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
-                    float4* __restrict__ partial4, int* __restrict__ done, int D, int L4) {
+                    float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4) {
+    extern __shared__ float4 ring_smem[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int stride = gridDim.x * wpb;
+    float4* ring = ring_smem + (size_t)(threadIdx.x >> 5) * RING * NCH * 32;
     const int n_items = __ldg(itemptr + D);
-    for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += stride) {
+    (void)wpb; (void)stride;
+    // dynamic work distribution: item costs range from 0 to CSC_CHUNK gathered rows, a static round-robin leaves
+    // half of the SMs idle behind the stragglers (ncu: sm__cycles_active.avg = 48 % of elapsed)
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
         const int c = __ldg(item_col + item);
         const int first_item = __ldg(itemptr + c);
         const int n_col_items = __ldg(itemptr + c + 1) - first_item;
@@ -305,7 +371,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
         float4 acc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < e) gather_accumulate<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, acc);
+        if (s < e) gather_accumulate_async<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, ring, acc);
         if (n_col_items == 1) {
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
@@ -350,7 +416,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
 }
 
 struct CscWorkspace {
-    int *colcnt, *done, *colptr, *cursor, *itemptr, *csc_row;
+    int *colcnt, *done, *next_item, *colptr, *cursor, *itemptr, *csc_row;
     int2* block_totals;
     int* item_col;
     float* csc_val;
@@ -363,6 +429,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     CscWorkspace w;
     w.colcnt = a.take<int>(D + 1);   // colcnt and done are contiguous: one memset clears both
     w.done = a.take<int>(D + 1);
+    w.next_item = a.take<int>(1);  // cleared together with colcnt / done
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
     w.itemptr = a.take<int>(D + 1);
@@ -379,9 +446,15 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
 template <int NCH>
 static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, cudaStream_t st) {
     const int blocks = sm_count() * 8;
-    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(w.colptr, w.itemptr, w.item_col, w.csc_row, w.csc_val,
+    const size_t smem = (size_t)(SPMM_THREADS / 32) * RING * NCH * 32 * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(dw_gather_v4_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, smem, st>>>(w.colptr, w.itemptr, w.item_col, w.csc_row, w.csc_val,
                                                             (const float4*)dH, (float4*)dW, (float4*)w.partial,
-                                                            w.done, D, L1 / 4);
+                                                            w.done, w.next_item, D, L1 / 4);
 }
 
 template <int NCH>
