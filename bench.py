@@ -163,6 +163,9 @@ def algorithmic_bytes(conf, nnz, P):
 
 
 def run_ours(args):
+    # NCCL prints its version banner on stdout: keep fd 1 clean for the single JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -220,8 +223,10 @@ def run_ours(args):
             tower.stage(dev_batches[i % NB])  # D2D copy of the batch into the staging CSR
             tower.train_step_staged()  # CUDA-graph replay of fwd+bwd+Adam
     else:
+        dp.capture_graph()
+
         def step(i):
-            dp.train_step(dev_batches[i % NB])
+            dp.train_step(dev_batches[i % NB])  # stage (D2D) + graph(fwd, dense bwd, CSC) + chunked gather/all-reduce/Adam
 
     for i in range(args.warmup):
         step(i)
@@ -256,10 +261,7 @@ def run_ours(args):
             sip.copy_(ip, non_blocking=True)
             six[:nnz].copy_(ix, non_blocking=True)
             svl[:nnz].copy_(vl, non_blocking=True)
-            from dssm_b200.ops import DeviceCSR
-
-            x = DeviceCSR(sip, six, svl, conf.rows, conf.TRIGRAM_D, nnz)
-            loss = dp.train_step(x)
+            loss = dp.train_step(None)  # runs on the staging CSR just uploaded
             host_loss.copy_(loss.view(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(host_loss[0])
@@ -327,13 +329,27 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": describe(conf, args.workload, world, {"mean_nnz_per_step_per_gpu": mean_nnz, "gemm_mode": conf.gemm_mode,
-                                                               "distinct_batches": NB, "cuda_graph": world == 1}),
+                                                               "distinct_batches": NB, "cuda_graph": True,
+                                                               "dp_w1_chunks": (dp.n_chunks if dp else None)}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms, "last_loss": last_loss},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: a process group that has collectives captured in a live CUDA graph can block forever in
+        # destroy_process_group (seen on NCCL 2.28.9: the JSON line was out, the ranks never exited).  Drop the
+        # graph first, meet at a barrier, and leave without the NCCL destructor if it does not return promptly.
+        torch.cuda.synchronize()
+        dp.graph = None
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(10.0, lambda: os._exit(0)).start()
+        try:
+            dist.destroy_process_group()
+        finally:
+            os._exit(0)
 
 
 def main():

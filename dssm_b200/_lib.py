@@ -68,6 +68,8 @@ SIGNATURES = {
     "dssm_spmm_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p]),
     "dssm_spmm_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64]),
     "dssm_spmm_bwd_dw": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
+    "dssm_spmm_bwd_csc_build": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _sz, _p]),
+    "dssm_spmm_bwd_dw_range": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _sz, _p]),
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
@@ -98,6 +100,13 @@ SIGNATURES = {
     "dssm_tower_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p]),
     "dssm_tower_backward": (C.c_int, [_p, _p]),
     "dssm_tower_adam": (C.c_int, [_p, _f, _p]),
+    "dssm_tower_backward_begin": (C.c_int, [_p, _p]),
+    "dssm_tower_backward_w1": (C.c_int, [_p, _i32, _i32, _p]),
+    "dssm_tower_w1_chunk": (C.c_int, [_p, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "dssm_tower_adam_range": (C.c_int, [_p, _i64, _i64, _f, _p]),
+    "dssm_tower_adam_advance": (C.c_int, [_p, _p]),
+    "dssm_tower_capture_graph_dp": (C.c_int, [_p, _p]),
+    "dssm_tower_fwd_bwd_begin_staged": (C.c_int, [_p, _p]),
     "dssm_tower_train_step": (C.c_int, [_p, _p, _p, _p, _p]),
     "dssm_tower_train_step_host": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
     "dssm_tower_capture_graph": (C.c_int, [_p, _p]),

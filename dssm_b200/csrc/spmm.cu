@@ -12,6 +12,7 @@ namespace dssm {
 constexpr int GATHER_UNROLL = 4;
 constexpr int SPMM_THREADS = 256;
 constexpr int CSC_CHUNK = 128;  // entries of one column handled by one warp in the dW1 gather
+constexpr int MAX_W1_CHUNKS = 64;  // column chunks the gather can be issued in (data-parallel comm overlap)
 
 // acc[k] += sum_{p in [s,e)} val[p] * src4[idx[p]*L4 + lane + 32k]   (sequential in p)
 template <int NCH>
@@ -347,19 +348,21 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ item_col,
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
-                    float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4) {
+                    float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4,
+                    int col_begin, int col_end) {
     extern __shared__ float4 ring_smem[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int stride = gridDim.x * wpb;
     float4* ring = ring_smem + (size_t)(threadIdx.x >> 5) * RING * NCH * 32;
-    const int n_items = __ldg(itemptr + D);
-    (void)wpb; (void)stride;
+    // items of the columns [col_begin, col_end): a contiguous item range (chunked gather for comm overlap)
+    const int item_lo = __ldg(itemptr + col_begin), n_items = __ldg(itemptr + col_end);
+    (void)wpb; (void)stride; (void)D;
     // dynamic work distribution: item costs range from 0 to CSC_CHUNK gathered rows, a static round-robin leaves
     // half of the SMs idle behind the stragglers (ncu: sm__cycles_active.avg = 48 % of elapsed)
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(next_item, 1);
+        if (lane == 0) item = item_lo + atomicAdd(next_item, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const int c = __ldg(item_col + item);
@@ -429,7 +432,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     CscWorkspace w;
     w.colcnt = a.take<int>(D + 1);   // colcnt and done are contiguous: one memset clears both
     w.done = a.take<int>(D + 1);
-    w.next_item = a.take<int>(1);  // cleared together with colcnt / done
+    w.next_item = a.take<int>(MAX_W1_CHUNKS);  // one work counter per column chunk; cleared together with colcnt / done
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
     w.itemptr = a.take<int>(D + 1);
@@ -444,8 +447,11 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
 }
 
 template <int NCH>
-static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, cudaStream_t st) {
-    const int blocks = sm_count() * 8;
+static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, int col_begin, int col_end,
+                             int chunk, cudaStream_t st) {
+    int blocks = sm_count() * 8;
+    const int cols = col_end - col_begin;
+    if (blocks > cols) blocks = cols > 0 ? cols : 1;
     const size_t smem = (size_t)(SPMM_THREADS / 32) * RING * NCH * 32 * sizeof(float4);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
@@ -454,7 +460,7 @@ static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, 
     }
     dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, smem, st>>>(w.colptr, w.itemptr, w.item_col, w.csc_row, w.csc_val,
                                                             (const float4*)dH, (float4*)dW, (float4*)w.partial,
-                                                            w.done, w.next_item, D, L1 / 4);
+                                                            w.done, w.next_item + chunk, D, L1 / 4, col_begin, col_end);
 }
 
 template <int NCH>
@@ -517,6 +523,67 @@ extern "C" size_t dssm_spmm_bwd_dw_workspace_bytes(int32_t R, int32_t D, int32_t
     return carve_csc(nullptr, D, L1, max_nnz).bytes;
 }
 
+static int csc_from_workspace(int D, int L1, void* workspace, size_t workspace_bytes, CscWorkspace* out) {
+    DSSM_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, DSSM_ERR_BAD_ALIGN,
+                 "spmm_bwd: workspace must be 256-byte aligned");
+    const size_t fixed = carve_csc(nullptr, D, L1, 0).bytes;
+    DSSM_REQUIRE(workspace_bytes >= fixed, DSSM_ERR_WORKSPACE, "spmm_bwd: workspace %zu < %zu", workspace_bytes, fixed);
+    // the caller sized the workspace for some max_nnz: recover the largest one whose carve fits (monotone)
+    int64_t lo = 0, hi = (int64_t)1 << 40;
+    while (hi - lo > 1) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (carve_csc(nullptr, D, L1, mid).bytes <= workspace_bytes) lo = mid; else hi = mid;
+    }
+    *out = carve_csc(workspace, D, L1, lo);
+    return DSSM_OK;
+}
+
+// Per-batch CSC of X (colptr / csc_row / csc_val / item table) into the workspace.  nnz lives on the device
+// (indptr[R]); the caller guarantees nnz <= the max_nnz the workspace was sized for.
+extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R,
+                                       int32_t D, int32_t L1, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(indptr && indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_csc_build: null pointer");
+    DSSM_REQUIRE(R > 0 && D > 0 && L1 > 0 && L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_csc_build: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    CscWorkspace w;
+    int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
+    if (rc != DSSM_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(w.colcnt, 0, (size_t)((char*)w.colptr - (char*)w.colcnt), st));
+    const int nsm = sm_count();
+    csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
+    LAUNCH_CHECK("csc_hist");
+    const int scan_blocks = cdiv(D, SCAN_TILE);
+    csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
+    LAUNCH_CHECK("csc_scan_local");
+    csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr,
+                                                              w.colcnt, w.item_col);
+    LAUNCH_CHECK("csc_scan_add");
+    const int wpb = SPMM_THREADS / 32;
+    int blocks = cdiv(R, wpb);
+    if (blocks > nsm * 32) blocks = nsm * 32;
+    csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.csc_row, w.csc_val);
+    LAUNCH_CHECK("csc_fill");
+    return DSSM_OK;
+}
+
+// dW1 rows [col_begin, col_end) from the CSC in the workspace (every row of the range is written).  `chunk` selects
+// the work counter; use a different chunk id (< 64) for every range issued after one csc_build.
+extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
+                                      int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(dH && dW1, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_range: null pointer");
+    DSSM_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= D, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_range: bad column range");
+    DSSM_REQUIRE(chunk >= 0 && chunk < MAX_W1_CHUNKS, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_range: chunk id out of range");
+    DSSM_REQUIRE(L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_dw_range: bad L1");
+    if (col_begin == col_end) return DSSM_OK;
+    CscWorkspace w;
+    int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
+    if (rc != DSSM_OK) return rc;
+    const int nch = cdiv(L1 / 4, 32);
+    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, col_begin, col_end, chunk, (cudaStream_t)stream));
+    LAUNCH_CHECK("dw_gather");
+    return DSSM_OK;
+}
+
 extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R,
                                 int32_t D, const float* dH, int32_t L1, float* dW1, int32_t method, void* workspace,
                                 size_t workspace_bytes, dssm_stream_t stream) {
@@ -544,41 +611,8 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
         LAUNCH_CHECK("spmm_bwd_scatter");
         return DSSM_OK;
     }
-    DSSM_REQUIRE(indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw: null indices/values");
-    DSSM_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, DSSM_ERR_BAD_ALIGN,
-                 "dssm_spmm_bwd_dw: workspace must be 256-byte aligned");
-    // capacity check: the caller sized the workspace for max_nnz; recover it from the byte count
-    const size_t fixed = carve_csc(nullptr, D, L1, 0).bytes;
-    DSSM_REQUIRE(workspace_bytes >= fixed, DSSM_ERR_WORKSPACE, "dssm_spmm_bwd_dw: workspace %zu < %zu", workspace_bytes, fixed);
-    // largest max_nnz whose carve fits (monotone): binary search on the host, cheap
-    int64_t lo = 0, hi = (int64_t)1 << 40;
-    while (hi - lo > 1) {
-        const int64_t mid = lo + (hi - lo) / 2;
-        if (carve_csc(nullptr, D, L1, mid).bytes <= workspace_bytes) lo = mid; else hi = mid;
-    }
-    const int64_t cap_nnz = lo;
-    CscWorkspace w = carve_csc(workspace, D, L1, cap_nnz);
-    // NOTE: nnz lives on the device (indptr[R]); the caller guarantees nnz <= the max_nnz it sized for.
-    CUDA_TRY(cudaMemsetAsync(w.colcnt, 0, (size_t)((char*)w.colptr - (char*)w.colcnt), st));
-    const int nsm = sm_count();
-    csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
-    LAUNCH_CHECK("csc_hist");
-    const int scan_blocks = cdiv(D, SCAN_TILE);
-    csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
-    LAUNCH_CHECK("csc_scan_local");
-    csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr,
-                                                              w.colcnt, w.item_col);
-    LAUNCH_CHECK("csc_scan_add");
-    {
-        const int wpb = SPMM_THREADS / 32;
-        int blocks = cdiv(R, wpb);
-        if (blocks > nsm * 32) blocks = nsm * 32;
-        csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.csc_row, w.csc_val);
-        LAUNCH_CHECK("csc_fill");
-    }
+    int rc = dssm_spmm_bwd_csc_build(indptr, indices, values, R, D, L1, workspace, workspace_bytes, stream);
+    if (rc != DSSM_OK) return rc;
     if (g_spmm_bwd_mid_event) CUDA_TRY(cudaEventRecord(g_spmm_bwd_mid_event, st));
-    const int nch = cdiv(L1 / 4, 32);
-    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, st));
-    LAUNCH_CHECK("dw_gather");
-    return DSSM_OK;
+    return dssm_spmm_bwd_dw_range(dH, D, L1, dW1, 0, D, 0, workspace, workspace_bytes, stream);
 }

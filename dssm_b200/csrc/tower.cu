@@ -67,6 +67,9 @@ struct dssm_tower {
     cudaGraph_t graph;
     cudaGraphExec_t graph_exec;
     int64_t launches_per_step;
+    cudaGraph_t graph_dp;  // forward + backward_begin (data-parallel pipeline)
+    cudaGraphExec_t graph_dp_exec;
+    int64_t launches_per_dp;
     int64_t launches;
 
     int find(const std::vector<TensorInfo>& v, const std::string& n) const {
@@ -195,6 +198,9 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->graph = nullptr;
     t->graph_exec = nullptr;
     t->launches_per_step = 0;
+    t->graph_dp = nullptr;
+    t->graph_dp_exec = nullptr;
+    t->launches_per_dp = 0;
     t->launches = 0;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
@@ -205,6 +211,8 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (!t) return;
     if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
     if (t->graph) cudaGraphDestroy(t->graph);
+    if (t->graph_dp_exec) cudaGraphExecDestroy(t->graph_dp_exec);
+    if (t->graph_dp) cudaGraphDestroy(t->graph_dp);
     delete t;
 }
 
@@ -216,6 +224,8 @@ extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nn
     dssm_tower tmp = *t;
     tmp.graph = nullptr;
     tmp.graph_exec = nullptr;
+    tmp.graph_dp = nullptr;
+    tmp.graph_dp_exec = nullptr;
     return tower_carve(&tmp, nullptr, max_nnz);
 }
 
@@ -255,6 +265,8 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     DSSM_REQUIRE(workspace_bytes >= need, DSSM_ERR_WORKSPACE, "dssm_tower_bind: workspace %zu < required %zu", workspace_bytes, need);
     if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
     if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+    if (t->graph_dp_exec) { cudaGraphExecDestroy(t->graph_dp_exec); t->graph_dp_exec = nullptr; }
+    if (t->graph_dp) { cudaGraphDestroy(t->graph_dp); t->graph_dp = nullptr; }
     t->params_p = params; t->grads_p = grads; t->m_p = m; t->v_p = v; t->ema_p = ema; t->beta_pow_p = beta_pow;
     t->ws = (char*)workspace;
     t->ws_bytes = workspace_bytes;
@@ -305,7 +317,14 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     return DSSM_OK;
 }
 
-static int tower_backward_impl(dssm_tower* t, dssm_stream_t s) {
+static void w1_chunk_cols(const dssm_tower* t, int chunk, int n_chunks, int* c0, int* c1) {
+    const int per = ((t->D + n_chunks - 1) / n_chunks + 3) / 4 * 4;  // multiple of 4 columns: float4-aligned slices
+    *c0 = chunk * per < t->D ? chunk * per : t->D;
+    *c1 = *c0 + per < t->D ? *c0 + per : t->D;
+}
+
+// w1_mode: 0 = whole dW1 here, 1 = stop after the CSC build (dssm_tower_backward_w1 produces dW1 chunk by chunk)
+static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) {
     const dssm_config& c = t->cfg;
     const int n = t->n_layers, R = t->R, B = t->B;
     for (int l = n; l >= 1; --l) {
@@ -327,11 +346,17 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s) {
                                t->fc_ws_bytes, s));
         } else {
             mark(PH_DENSE_BWD);
-            if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];
-            const int rc = dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1],
-                                            t->G_("W1"), 0, t->sp_ws, t->sp_ws_bytes, s);
-            g_spmm_bwd_mid_event = nullptr;
-            TRY(rc);
+            if (w1_mode == 1) {
+                DSSM_REQUIRE(t->L[1] % 4 == 0 && t->L[1] <= 1024, DSSM_ERR_BAD_SHAPE, "chunked dW1 needs L1 %% 4 == 0");
+                TRY(dssm_spmm_bwd_csc_build(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->L[1], t->sp_ws,
+                                            t->sp_ws_bytes, s));
+            } else {
+                if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];
+                const int rc = dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1],
+                                                t->G_("W1"), 0, t->sp_ws, t->sp_ws_bytes, s);
+                g_spmm_bwd_mid_event = nullptr;
+                TRY(rc);
+            }
             mark(PH_DW_GATHER);
             TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
             mark(PH_B1);
@@ -370,6 +395,51 @@ extern "C" int dssm_tower_backward(dssm_tower* t, dssm_stream_t stream) {
     LaunchScope ls(t);
     t->fwd_train_done = false;
     return tower_backward_impl(t, stream);
+}
+
+extern "C" int dssm_tower_backward_begin(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_backward_begin: tower not bound");
+    DSSM_REQUIRE(t->grads_p, DSSM_ERR_STATE, "dssm_tower_backward_begin: no grads buffer bound");
+    DSSM_REQUIRE(t->fwd_train_done, DSSM_ERR_STATE, "dssm_tower_backward_begin: needs a preceding training-mode forward");
+    LaunchScope ls(t);
+    t->fwd_train_done = false;
+    return tower_backward_impl(t, stream, 1);
+}
+
+extern "C" int dssm_tower_w1_chunk(const dssm_tower* t, int32_t chunk, int32_t n_chunks, int64_t* offset_floats, int64_t* count_floats) {
+    DSSM_REQUIRE(t && n_chunks > 0 && n_chunks <= 64 && chunk >= 0 && chunk < n_chunks, DSSM_ERR_BAD_ARG, "dssm_tower_w1_chunk: bad chunk");
+    int c0, c1;
+    w1_chunk_cols(t, chunk, n_chunks, &c0, &c1);
+    if (offset_floats) *offset_floats = t->params[t->find(t->params, "W1")].off + (int64_t)c0 * t->L[1];
+    if (count_floats) *count_floats = (int64_t)(c1 - c0) * t->L[1];
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_backward_w1(dssm_tower* t, int32_t chunk, int32_t n_chunks, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && t->grads_p, DSSM_ERR_STATE, "dssm_tower_backward_w1: tower not bound");
+    DSSM_REQUIRE(n_chunks > 0 && n_chunks <= 64 && chunk >= 0 && chunk < n_chunks, DSSM_ERR_BAD_ARG, "dssm_tower_backward_w1: bad chunk");
+    LaunchScope ls(t);
+    int c0, c1;
+    w1_chunk_cols(t, chunk, n_chunks, &c0, &c1);
+    return dssm_spmm_bwd_dw_range(t->dh[1], t->D, t->L[1], t->G_("W1"), c0, c1, chunk, t->sp_ws, t->sp_ws_bytes, stream);
+}
+
+extern "C" int dssm_tower_adam_range(dssm_tower* t, int64_t offset_floats, int64_t count_floats, float grad_scale,
+                                     dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_adam_range: tower not bound");
+    DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_adam_range: optimizer buffers not bound");
+    DSSM_REQUIRE(offset_floats >= 0 && count_floats >= 0 && offset_floats + count_floats <= t->P && offset_floats % 4 == 0,
+                 DSSM_ERR_BAD_ARG, "dssm_tower_adam_range: bad range");
+    LaunchScope ls(t);
+    const dssm_config& c = t->cfg;
+    return dssm_adam_step(t->params_p + offset_floats, t->grads_p + offset_floats, t->m_p + offset_floats, t->v_p + offset_floats,
+                          count_floats, t->beta_pow_p, c.learning_rate, c.beta1, c.beta2, c.adam_eps, grad_scale, stream);
+}
+
+extern "C" int dssm_tower_adam_advance(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_adam_advance: tower not bound");
+    LaunchScope ls(t);
+    return dssm_adam_advance(t->beta_pow_p, t->cfg.beta1, t->cfg.beta2, stream);
 }
 
 extern "C" int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t stream) {
@@ -426,6 +496,46 @@ extern "C" int dssm_tower_capture_graph(dssm_tower* t, dssm_stream_t stream) {
     t->graph = g;
     CUDA_TRY(cudaGraphInstantiate(&t->graph_exec, t->graph, 0));
     return DSSM_OK;
+}
+
+// Data-parallel pipeline, first half: training forward + backward_begin on the staging CSR, as one CUDA graph.
+extern "C" int dssm_tower_capture_graph_dp(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && t->grads_p, DSSM_ERR_STATE, "dssm_tower_capture_graph_dp: tower not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSSM_REQUIRE(st != nullptr, DSSM_ERR_BAD_ARG, "dssm_tower_capture_graph_dp: needs a non-default stream");
+    if (t->graph_dp_exec) { cudaGraphExecDestroy(t->graph_dp_exec); t->graph_dp_exec = nullptr; }
+    if (t->graph_dp) { cudaGraphDestroy(t->graph_dp); t->graph_dp = nullptr; }
+    const int64_t before = g_launch_count;
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = tower_forward_impl(t, t->st_indptr, t->st_indices, t->st_values, 1, 1, true, stream);
+    if (rc == DSSM_OK) rc = tower_backward_impl(t, stream, 1);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    t->fwd_train_done = false;
+    if (rc != DSSM_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail(DSSM_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    t->launches_per_dp = g_launch_count - before;
+    t->graph_dp = g;
+    CUDA_TRY(cudaGraphInstantiate(&t->graph_dp_exec, t->graph_dp, 0));
+    return DSSM_OK;
+}
+
+// forward (training) + backward_begin on the staging CSR; graph replay when captured
+extern "C" int dssm_tower_fwd_bwd_begin_staged(dssm_tower* t, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && t->grads_p, DSSM_ERR_STATE, "dssm_tower_fwd_bwd_begin_staged: tower not bound");
+    if (t->graph_dp_exec) {
+        CUDA_TRY(cudaGraphLaunch(t->graph_dp_exec, (cudaStream_t)stream));
+        t->launches += t->launches_per_dp;
+        t->cur_indptr = t->st_indptr; t->cur_indices = t->st_indices; t->cur_values = t->st_values;
+        return DSSM_OK;
+    }
+    LaunchScope ls(t);
+    TRY(tower_forward_impl(t, t->st_indptr, t->st_indices, t->st_values, 1, 1, true, stream));
+    t->fwd_train_done = false;
+    return tower_backward_impl(t, stream, 1);
 }
 
 extern "C" int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream) {

@@ -42,24 +42,94 @@ def allreduce_mean_(tensors: List[torch.Tensor], group=None) -> None:
 
 
 class DataParallelTower:
-    """Wraps a DSSMTower: forward+backward locally, all-reduce of the flat grads (+ EMA), Adam with 1/world."""
+    """Wraps a DSSMTower.  Per step: local forward and dense backward, then the dW1 gather is issued in `n_chunks`
+    column chunks; the NCCL all-reduce (AVG) of chunk k -- a contiguous slice of the flat gradient buffer -- runs on
+    NCCL's stream while chunk k+1 is being gathered, and Adam on chunk k runs while chunk k+1 is still on the wire.
+    The small gradients (FC2.., BN) and the EMA shadows live behind W1 in the same allocation and go out first as ONE
+    collective.  Equals one Adam step on the mean gradient (oracle/dssm_oracle.py:DPOracle).
+    capture_graph() records the whole step -- kernels and collectives -- into one CUDA graph, so the ~60 launches
+    cost no CPU time per step."""
 
-    def __init__(self, tower, group=None):
+    def __init__(self, tower, group=None, n_chunks: int = 2):
         self.tower = tower
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_chunks = max(1, min(int(n_chunks), 64))
+        off, rows, cols = tower._layout[0]["W1"]
+        self.w1_end = off + ((rows * cols + 3) // 4) * 4
+        self.pipelined = tower.conf.layers[0] % 4 == 0 and off == 0
+        self.graph = None
+        self.graphed = False
         # identical starting parameters on every rank
         if self.world > 1:
             dist.broadcast(tower.params, src=0, group=group)
 
-    def train_step(self, x) -> torch.Tensor:
+    # ---- one step on the staging CSR -------------------------------------------------------------------
+    def _step_staged(self) -> None:
+        t, n = self.tower, self.n_chunks
+        t.fwd_bwd_begin_staged()
+        if self.world == 1:
+            for k in range(n):
+                t.backward_w1(k, n)
+            t.adam(grad_scale=1.0)
+            return
+        # [grads beyond W1 | EMA shadows] are contiguous in tower.comm: one collective
+        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        works = []
+        for k in range(n):
+            t.backward_w1(k, n)
+            off, cnt = t.w1_chunk(k, n)
+            if cnt:
+                works.append((off, cnt, dist.all_reduce(t.grads[off:off + cnt], op=dist.ReduceOp.AVG, group=self.group, async_op=True)))
+        for off, cnt, w in works:
+            w.wait()
+            t.adam_range(off, cnt, 1.0)
+        w_rest.wait()
+        t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
+        t.adam_advance()
+
+    def capture_graph(self, warmup: int = 3) -> None:
+        """Record the staged step (compute + collectives) into one CUDA graph; falls back to graphing only the compute
+        half (C side) if the collectives cannot be captured."""
+        if not self.pipelined:
+            return
         t = self.tower
-        loss = t.forward(x, on_train=True)
-        t.backward()
-        if self.world > 1:
-            dist.all_reduce(t.grads, op=dist.ReduceOp.SUM, group=self.group)
-            if t.conf.use_bn:
-                dist.all_reduce(t.ema, op=dist.ReduceOp.SUM, group=self.group)
-                t.ema.mul_(1.0 / self.world)
-        t.adam(grad_scale=1.0 / self.world)
-        return loss
+        try:
+            s = torch.cuda.Stream(device=t.device)
+            s.wait_stream(torch.cuda.current_stream(t.device))
+            with torch.cuda.stream(s):
+                for _ in range(warmup):  # communicators, attribute calls, allocator warm-up outside the capture
+                    self._step_staged()
+            torch.cuda.current_stream(t.device).wait_stream(s)
+            torch.cuda.synchronize(t.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._step_staged()
+            self.graph = g
+        except Exception as e:  # pragma: no cover - depends on the NCCL / driver combination
+            import sys
+
+            print(f"[dssm_b200] whole-step graph capture failed ({type(e).__name__}: {e}); graphing the compute half only",
+                  file=sys.stderr)
+            self.graph = None
+            torch.cuda.synchronize(t.device)
+            t.capture_graph_dp()
+        self.graphed = True
+
+    def train_step(self, x=None) -> torch.Tensor:
+        """x: a DeviceCSR, or None to run on whatever is in the tower's staging CSR (tower.stage / staging_views)."""
+        t = self.tower
+        if not self.pipelined:
+            loss = t.forward(x, on_train=True)
+            t.backward()
+            if self.world > 1:
+                dist.all_reduce(t.comm, op=dist.ReduceOp.AVG, group=self.group)
+            t.adam(grad_scale=1.0)
+            return loss
+        if x is not None:
+            t.stage(x)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_staged()
+        return t.tensor("loss")

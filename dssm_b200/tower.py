@@ -66,7 +66,11 @@ class DSSMTower:
         self.E = lib.dssm_tower_ema_count(self._h)
         with torch.cuda.device(self.device):
             z = lambda n: torch.zeros(max(int(n), 4), dtype=torch.float32, device=self.device)
-            self.params, self.grads, self.m, self.v, self.ema = z(self.P), z(self.P), z(self.P), z(self.P), z(self.E)
+            self.params, self.m, self.v = z(self.P), z(self.P), z(self.P)
+            # grads and the EMA shadows share one allocation so that data-parallel training exchanges
+            # [small gradients | EMA] with a single collective (dssm_b200/parallel.py)
+            self.comm = z(self.P + max(self.E, 4))
+            self.grads, self.ema = self.comm[:self.P], self.comm[self.P:self.P + max(self.E, 4)]
             self.beta_pow = torch.tensor([conf.beta1, conf.beta2], dtype=torch.float32, device=self.device)
             ws_bytes = lib.dssm_tower_workspace_bytes(self._h, self.max_nnz)
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
@@ -224,6 +228,38 @@ class DSSMTower:
 
     def adam(self, grad_scale: float = 1.0) -> None:
         check(lib.dssm_tower_adam(self._h, float(grad_scale), stream_ptr()))
+
+    # pipelined pieces for data-parallel training (dssm_b200/parallel.py)
+    def backward_begin(self) -> None:
+        """Backward without the dW1 gather: dense layers, small gradients, CSC build."""
+        check(lib.dssm_tower_backward_begin(self._h, stream_ptr()))
+
+    def backward_w1(self, chunk: int, n_chunks: int) -> None:
+        """dW1 rows of column chunk `chunk` of `n_chunks` (a contiguous slice of the flat gradient buffer)."""
+        check(lib.dssm_tower_backward_w1(self._h, chunk, n_chunks, stream_ptr()))
+
+    def w1_chunk(self, chunk: int, n_chunks: int):
+        off, cnt = C.c_int64(), C.c_int64()
+        check(lib.dssm_tower_w1_chunk(self._h, chunk, n_chunks, C.byref(off), C.byref(cnt)))
+        return off.value, cnt.value
+
+    def adam_range(self, offset: int, count: int, grad_scale: float = 1.0) -> None:
+        check(lib.dssm_tower_adam_range(self._h, offset, count, float(grad_scale), stream_ptr()))
+
+    def adam_advance(self) -> None:
+        check(lib.dssm_tower_adam_advance(self._h, stream_ptr()))
+
+    def capture_graph_dp(self) -> None:
+        """Capture training forward + backward_begin on the staging CSR into a CUDA graph."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            check(lib.dssm_tower_capture_graph_dp(self._h, s.cuda_stream))
+        torch.cuda.current_stream(self.device).wait_stream(s)
+
+    def fwd_bwd_begin_staged(self) -> torch.Tensor:
+        check(lib.dssm_tower_fwd_bwd_begin_staged(self._h, stream_ptr()))
+        return self.tensor("loss")
 
     def train_step(self, x: DeviceCSR) -> torch.Tensor:
         """sess.run(train_step, feed_dict=pull_batch(True, ...)) -- new_dssm.py:267-269.  Device CSR in, device loss out."""

@@ -103,6 +103,14 @@ int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float*
                      const float* dH, int32_t L1, float* dW1, int32_t method, void* workspace,
                      size_t workspace_bytes, dssm_stream_t stream);
 
+/* The two halves of method 0, for callers that overlap the gradient exchange with the gather (data-parallel
+ * training): build the per-batch CSC once, then produce dW1 rows [col_begin, col_end) range by range (each range
+ * a contiguous slice of dW1; `chunk` < 64 must differ between ranges issued after one build).  L1 % 4 == 0. */
+int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
+                            int32_t L1, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
+                           int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
  * (query segment rows [0,B), doc segment rows [B,R)) in one call.
@@ -242,6 +250,20 @@ int dssm_tower_forward(dssm_tower* t, const int32_t* indptr, const int32_t* indi
 int dssm_tower_backward(dssm_tower* t, dssm_stream_t stream);
 /* Adam on the bound buffers; grad_scale multiplies the grads first (data-parallel average). */
 int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t stream);
+/* Data-parallel pipeline: dssm_tower_backward_begin = everything of the backward except the dW1 gather (dense
+ * layers, small gradients, CSC build); dssm_tower_backward_w1(chunk k of n) = dW1 rows of column chunk k;
+ * dssm_tower_adam_range = Adam over params[offset, offset+count) without advancing the beta powers;
+ * dssm_tower_adam_advance advances them once per step.  Chunk k of n covers columns [k*ceil(D/n), ...) = the
+ * contiguous float range reported by dssm_tower_w1_chunk. */
+int dssm_tower_backward_begin(dssm_tower* t, dssm_stream_t stream);
+int dssm_tower_backward_w1(dssm_tower* t, int32_t chunk, int32_t n_chunks, dssm_stream_t stream);
+int dssm_tower_w1_chunk(const dssm_tower* t, int32_t chunk, int32_t n_chunks, int64_t* offset_floats, int64_t* count_floats);
+int dssm_tower_adam_range(dssm_tower* t, int64_t offset_floats, int64_t count_floats, float grad_scale, dssm_stream_t stream);
+int dssm_tower_adam_advance(dssm_tower* t, dssm_stream_t stream);
+/* Training forward + dssm_tower_backward_begin on the staging CSR; dssm_tower_capture_graph_dp turns that pair into
+ * one CUDA graph that dssm_tower_fwd_bwd_begin_staged replays (the per-step CPU cost of ~40 launches disappears). */
+int dssm_tower_capture_graph_dp(dssm_tower* t, dssm_stream_t stream);
+int dssm_tower_fwd_bwd_begin_staged(dssm_tower* t, dssm_stream_t stream);
 /* sess.run(train_step, feed_dict=pull_batch(True, ...)) -- new_dssm.py:267-269: forward + backward + Adam. */
 int dssm_tower_train_step(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
                           dssm_stream_t stream);
