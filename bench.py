@@ -136,9 +136,13 @@ def run_reference(args):
     batches = [make_batch(conf, seed=s) for s in range(2)]
     params = init_params(conf, 0)
     threads = host_threads()
-    for _ in range(max(args.warmup - 1, 0)):
-        cpu_port_step_time(conf, batches[:1], params, 0, threads)
-    times = cpu_port_step_time(conf, batches, params, args.steps, threads)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host thread
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=threads):
+        for _ in range(max(args.warmup - 1, 0)):
+            cpu_port_step_time(conf, batches[:1], params, 0, threads)
+        times = cpu_port_step_time(conf, batches, params, args.steps, threads)
     ms = 1e3 * float(np.mean(times))
     value = conf.query_BS / (ms / 1e3)
     sample = f"{args.steps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy port, single process"
@@ -318,7 +322,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         nsteps = 6 if conf.query_BS <= 1024 else 2
-        times = cpu_port_step_time(conf, batches[:2], params, nsteps, threads)
+        from threadpoolctl import threadpool_limits
+
+        with threadpool_limits(limits=threads):
+            times = cpu_port_step_time(conf, batches[:2], params, nsteps, threads)
         cpu = {"value": conf.query_BS / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{nsteps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy oracle "
                          f"(scipy CSR @ is single-threaded, dense layers on OpenBLAS threads)",
