@@ -252,7 +252,8 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_PER_THREAD = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
 
-__device__ __forceinline__ int items_of(int n) { return max(1, (n + CSC_CHUNK - 1) / CSC_CHUNK); }
+// work items of a column: ceil(cnt / CSC_CHUNK); empty columns have none (their dW1 rows are zero-filled by a memset)
+__device__ __forceinline__ int items_of(int n) { return (n + CSC_CHUNK - 1) / CSC_CHUNK; }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 csc_scan_local_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ colptr, int* __restrict__ itemptr,
@@ -295,7 +296,7 @@ csc_scan_local_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ c
 __global__ void __launch_bounds__(SCAN_THREADS)
 csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, int* __restrict__ colptr,
                     int* __restrict__ cursor, int* __restrict__ itemptr, const int* __restrict__ colcnt,
-                    int* __restrict__ item_col) {
+                    int4* __restrict__ item_rec) {
     __shared__ int2 red[SCAN_THREADS / 32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     int oa = 0, ob = 0;
@@ -317,8 +318,12 @@ csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, 
             cursor[col] = p;
             const int first = itemptr[col] + ob;
             itemptr[col] = first;
-            const int ni = items_of(colcnt[col]);  // item -> column map, so the gather needs no search
-            for (int i = 0; i < ni; ++i) item_col[first + i] = col;
+            // one record per item {column, first entry, end entry, items of the column}: the gather reads it with
+            // a single 16-byte load instead of chasing item -> column -> colptr
+            const int cnt = colcnt[col];
+            const int ni = items_of(cnt);
+            for (int i = 0; i < ni; ++i)
+                item_rec[first + i] = make_int4(col, p + i * CSC_CHUNK, min(p + cnt, p + (i + 1) * CSC_CHUNK), ni);
         }
     }
     if ((int)blockIdx.x == n_blocks - 1 && t == 0) {
@@ -345,7 +350,7 @@ csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 
 template <int NCH>
 __global__ void __launch_bounds__(SPMM_THREADS)
-dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int* __restrict__ item_col,
+dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int4* __restrict__ item_rec,
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
                     float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4,
@@ -365,12 +370,8 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
         if (lane == 0) item = item_lo + atomicAdd(next_item, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int c = __ldg(item_col + item);
-        const int first_item = __ldg(itemptr + c);
-        const int n_col_items = __ldg(itemptr + c + 1) - first_item;
-        const int cs = __ldg(colptr + c), ce = __ldg(colptr + c + 1);
-        const int s = cs + (item - first_item) * CSC_CHUNK;
-        const int e = min(ce, s + CSC_CHUNK);
+        const int4 rec = __ldg(item_rec + item);
+        const int c = rec.x, s = rec.y, e = rec.z, n_col_items = rec.w;
         float4 acc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -394,6 +395,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
             prev = __shfl_sync(0xffffffffu, prev, 0);
             if (prev == n_col_items - 1) {  // last item of the column: fold the partials in item order
                 __threadfence();
+                const int first_item = item - (s - __ldg(colptr + c)) / CSC_CHUNK;
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
@@ -421,7 +423,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
 struct CscWorkspace {
     int *colcnt, *done, *next_item, *colptr, *cursor, *itemptr, *csc_row;
     int2* block_totals;
-    int* item_col;
+    int4* item_rec;
     float* csc_val;
     float* partial;
     size_t bytes;
@@ -440,7 +442,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.csc_row = a.take<int>((size_t)max_nnz);
     w.csc_val = a.take<float>((size_t)max_nnz);
     const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
-    w.item_col = a.take<int>(max_items);
+    w.item_rec = a.take<int4>(max_items);
     w.partial = a.take<float>(max_items * (size_t)L1);
     w.bytes = a.off;
     return w;
@@ -458,7 +460,7 @@ static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, 
         cudaFuncSetAttribute(dw_gather_v4_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, smem, st>>>(w.colptr, w.itemptr, w.item_col, w.csc_row, w.csc_val,
+    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, smem, st>>>(w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val,
                                                             (const float4*)dH, (float4*)dW, (float4*)w.partial,
                                                             w.done, w.next_item + chunk, D, L1 / 4, col_begin, col_end);
 }
@@ -541,7 +543,8 @@ static int csc_from_workspace(int D, int L1, void* workspace, size_t workspace_b
 // Per-batch CSC of X (colptr / csc_row / csc_val / item table) into the workspace.  nnz lives on the device
 // (indptr[R]); the caller guarantees nnz <= the max_nnz the workspace was sized for.
 extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R,
-                                       int32_t D, int32_t L1, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
+                                       int32_t D, int32_t L1, float* dW1, void* workspace, size_t workspace_bytes,
+                                       dssm_stream_t stream) {
     DSSM_REQUIRE(indptr && indices && values, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_csc_build: null pointer");
     DSSM_REQUIRE(R > 0 && D > 0 && L1 > 0 && L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_csc_build: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -549,6 +552,8 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
     if (rc != DSSM_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(w.colcnt, 0, (size_t)((char*)w.colptr - (char*)w.colcnt), st));
+    // rows of dW1 whose column is absent from the batch have no work item: they are zero-filled here
+    if (dW1) CUDA_TRY(cudaMemsetAsync(dW1, 0, (size_t)D * L1 * sizeof(float), st));
     const int nsm = sm_count();
     csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
     LAUNCH_CHECK("csc_hist");
@@ -556,7 +561,7 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
     LAUNCH_CHECK("csc_scan_local");
     csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr,
-                                                              w.colcnt, w.item_col);
+                                                              w.colcnt, w.item_rec);
     LAUNCH_CHECK("csc_scan_add");
     const int wpb = SPMM_THREADS / 32;
     int blocks = cdiv(R, wpb);
@@ -611,7 +616,7 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
         LAUNCH_CHECK("spmm_bwd_scatter");
         return DSSM_OK;
     }
-    int rc = dssm_spmm_bwd_csc_build(indptr, indices, values, R, D, L1, workspace, workspace_bytes, stream);
+    int rc = dssm_spmm_bwd_csc_build(indptr, indices, values, R, D, L1, dW1, workspace, workspace_bytes, stream);
     if (rc != DSSM_OK) return rc;
     if (g_spmm_bwd_mid_event) CUDA_TRY(cudaEventRecord(g_spmm_bwd_mid_event, st));
     return dssm_spmm_bwd_dw_range(dH, D, L1, dW1, 0, D, 0, workspace, workspace_bytes, stream);

@@ -67,6 +67,11 @@ struct dssm_tower {
     cudaGraph_t graph;
     cudaGraphExec_t graph_exec;
     int64_t launches_per_step;
+    // The per-batch CSC of X depends only on the input batch: it is built on a side stream, forked at the start
+    // of the training forward and joined right before the dW1 gather (also inside graph capture).
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
+    bool csc_forked;
     cudaGraph_t graph_dp;  // forward + backward_begin (data-parallel pipeline)
     cudaGraphExec_t graph_dp_exec;
     int64_t launches_per_dp;
@@ -201,6 +206,10 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->graph_dp = nullptr;
     t->graph_dp_exec = nullptr;
     t->launches_per_dp = 0;
+    t->side = nullptr;
+    t->ev_fork = nullptr;
+    t->ev_join = nullptr;
+    t->csc_forked = false;
     t->launches = 0;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
@@ -213,6 +222,9 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (t->graph) cudaGraphDestroy(t->graph);
     if (t->graph_dp_exec) cudaGraphExecDestroy(t->graph_dp_exec);
     if (t->graph_dp) cudaGraphDestroy(t->graph_dp);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->side) cudaStreamDestroy(t->side);
     delete t;
 }
 
@@ -226,6 +238,9 @@ extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nn
     tmp.graph_exec = nullptr;
     tmp.graph_dp = nullptr;
     tmp.graph_dp_exec = nullptr;
+    tmp.side = nullptr;
+    tmp.ev_fork = nullptr;
+    tmp.ev_join = nullptr;
     return tower_carve(&tmp, nullptr, max_nnz);
 }
 
@@ -272,6 +287,12 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     t->ws_bytes = workspace_bytes;
     t->max_nnz = max_nnz;
     tower_carve(t, t->ws, max_nnz);
+    if (!t->side) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    }
+    t->csc_forked = false;
     t->bound = true;
     t->fwd_train_done = false;
     return DSSM_OK;
@@ -288,6 +309,17 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     const dssm_config& c = t->cfg;
     const int n = t->n_layers, R = t->R, B = t->B;
     mark(PH_START);
+    t->csc_forked = false;
+    if (want_grad && on_train && t->L[1] % 4 == 0 && t->L[1] <= 1024 && !(g_timer && g_timer->on)) {
+        // fork: CSC build on the side stream, concurrent with the whole forward and the dense backward
+        cudaStream_t main_st = (cudaStream_t)s;
+        CUDA_TRY(cudaEventRecord(t->ev_fork, main_st));
+        CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
+        TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1], t->grads_p ? t->G_("W1") : nullptr, t->sp_ws,
+                                    t->sp_ws_bytes, (dssm_stream_t)t->side));
+        CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
+        t->csc_forked = true;
+    }
     TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
     mark(PH_SPMM_FWD);
     for (int l = 1; l <= n; ++l) {
@@ -346,9 +378,14 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
                                t->fc_ws_bytes, s));
         } else {
             mark(PH_DENSE_BWD);
-            if (w1_mode == 1) {
+            if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
+                CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join, 0));
+                t->csc_forked = false;
+                if (w1_mode == 0)
+                    TRY(dssm_spmm_bwd_dw_range(t->dh[1], t->D, t->L[1], t->G_("W1"), 0, t->D, 0, t->sp_ws, t->sp_ws_bytes, s));
+            } else if (w1_mode == 1) {
                 DSSM_REQUIRE(t->L[1] % 4 == 0 && t->L[1] <= 1024, DSSM_ERR_BAD_SHAPE, "chunked dW1 needs L1 %% 4 == 0");
-                TRY(dssm_spmm_bwd_csc_build(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->L[1], t->sp_ws,
+                TRY(dssm_spmm_bwd_csc_build(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->L[1], t->G_("W1"), t->sp_ws,
                                             t->sp_ws_bytes, s));
             } else {
                 if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];

@@ -105,9 +105,11 @@ int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float*
 
 /* The two halves of method 0, for callers that overlap the gradient exchange with the gather (data-parallel
  * training): build the per-batch CSC once, then produce dW1 rows [col_begin, col_end) range by range (each range
- * a contiguous slice of dW1; `chunk` < 64 must differ between ranges issued after one build).  L1 % 4 == 0. */
+ * a contiguous slice of dW1; `chunk` < 64 must differ between ranges issued after one build).  L1 % 4 == 0.
+ * The build zero-fills dW1; the ranges then write the rows of the columns present in the batch. */
 int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
-                            int32_t L1, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+                            int32_t L1, float* dW1 /* zero-filled here: rows of absent columns get no other write */,
+                            void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
                            int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 
