@@ -73,7 +73,7 @@ SIGNATURES = {
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
-    "dssm_bn_act_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "dssm_bn_act_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_fc_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dssm_fc_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
     "dssm_fc_bwd_dx": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
@@ -84,6 +84,7 @@ SIGNATURES = {
     "dssm_merge_negative_doc": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "dssm_merge_negative_doc_index": (C.c_int, [_i32, _i32, _p, _p]),
     "dssm_cos_softmax_loss": (C.c_int, [_p, _i32, _i32, _i32, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dssm_cos_softmax_loss_fused": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _i32, _i32, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dssm_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
     "dssm_adam_advance": (C.c_int, [_p, _f, _f, _p]),
     "dssm_corpus_topk_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),

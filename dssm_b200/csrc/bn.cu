@@ -170,6 +170,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
                      const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
     __shared__ float red0[BN_TY][BN_TX + 1];
     __shared__ float red1[BN_TY][BN_TX + 1];
+    __shared__ float red2[BN_TY][BN_TX + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
     const int nq = bn_chunks_of(B, chunk_rows);
@@ -179,7 +180,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
     } else {
         seg = 1; r0 = B + (chunk - nq) * chunk_rows; r1 = min(R, r0 + chunk_rows);
     }
-    float sg = 0.f, sgx = 0.f;
+    float sg = 0.f, sgx = 0.f, sx = 0.f;
     if (col < L) {
         const int o = seg * L + col;
         const float mu = __ldg(mean + o), rs = __ldg(rstd + o), sc = __ldg(scale + o), sh = __ldg(shift + o);
@@ -195,50 +196,71 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
             for (int u = 0; u < MLP; ++u) {
                 const float a = act_fwd(fmaf(hv[u], sc, sh), act);
                 const float g = dv[u] * act_grad_from_out(a, act);
+                const float xh = (hv[u] - mu) * rs;
                 sg += g;
-                sgx = fmaf(g, (hv[u] - mu) * rs, sgx);
+                sgx = fmaf(g, xh, sgx);
+                sx += xh;
             }
         }
         for (; r < r1; r += BN_TY) {
             const float h = __ldg(H + (size_t)r * L + col);
             const float a = act_fwd(fmaf(h, sc, sh), act);
             const float g = __ldg(dA + (size_t)r * L + col) * act_grad_from_out(a, act);
+            const float xh = (h - mu) * rs;
             sg += g;
-            sgx = fmaf(g, (h - mu) * rs, sgx);
+            sgx = fmaf(g, xh, sgx);
+            sx += xh;
         }
     }
     red0[ty][tx] = sg;
     red1[ty][tx] = sgx;
+    red2[ty][tx] = sx;
     __syncthreads();
     if (ty == 0 && col < L) {
-        float t0 = 0.f, t1 = 0.f;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < BN_TY; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
+        for (int i = 0; i < BN_TY; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; t2 += red2[i][tx]; }
         part[((size_t)0 * n_chunks_total + chunk) * L + col] = t0;
         part[((size_t)1 * n_chunks_total + chunk) * L + col] = t1;
+        part[((size_t)2 * n_chunks_total + chunk) * L + col] = t2;
     }
 }
 
+// dgamma, dbeta per (segment, column); optionally the pre-BN bias gradient db[c] = sum_r dH[r,c].  Under BN that sum
+// is identically  -gamma*rstd*dgamma*(sum_r xhat)/n  per segment (the g and dbeta terms cancel exactly), i.e. rounding
+// noise around zero -- evaluated here from sum xhat accumulated in the same pass instead of another sweep over dH.
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
+bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, int B, int R,
+                       const float* __restrict__ gamma, const float* __restrict__ rstd, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ db_seg /* [2][L] or NULL */) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= 2 * L) return;
     const int seg = i / L, col = i - seg * L;
     const int c0 = seg == 0 ? 0 : nq_chunks;
     const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
-    float b = 0.f, g = 0.f;
+    float b = 0.f, g = 0.f, x = 0.f;
     for (int c = c0 + lane; c < c1; c += 32) {
         b += part[((size_t)0 * n_chunks_total + c) * L + col];
         g += part[((size_t)1 * n_chunks_total + c) * L + col];
+        x += part[((size_t)2 * n_chunks_total + c) * L + col];
     }
     b = warp_sum(b);
     g = warp_sum(g);
+    x = warp_sum(x);
     if (lane == 0) {
         dbeta[i] = b;
         dgamma[i] = g;
+        if (db_seg) {
+            const float n = seg == 0 ? (float)B : (float)(R - B);
+            db_seg[i] = n > 0.f ? -(gamma[i] * rstd[i]) * g * (x / n) : 0.f;
+        }
     }
+}
+
+__global__ void db_combine_kernel(const float* __restrict__ db_seg, int L, float* __restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < L) db[c] = db_seg[c] + db_seg[L + c];
 }
 
 // pass 2 (in place): dH = gamma*rstd * (g - dbeta/n - xhat*dgamma/n)
@@ -301,7 +323,7 @@ extern "C" size_t dssm_bn_workspace_bytes(int32_t R, int32_t L) {
     if (R <= 0 || L <= 0) return 0;
     // worst case split of R rows into two segments adds one chunk
     const size_t chunks = (size_t)bn_chunks_of(R) + 2;
-    return align_up(3 * chunks * (size_t)L * sizeof(float), 256);
+    return align_up((3 * chunks + 2) * (size_t)L * sizeof(float), 256);
 }
 
 extern "C" int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, int32_t on_train, int32_t update_ema,
@@ -341,7 +363,7 @@ extern "C" int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B
 
 extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act,
                                     const float* gamma, const float* mean, const float* rstd, const float* scale,
-                                    const float* shift, float* dgamma, float* dbeta, void* workspace,
+                                    const float* shift, float* dgamma, float* dbeta, float* db, void* workspace,
                                     size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(dA && H, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null pointer");
     DSSM_REQUIRE(R > 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: bad shape");
@@ -355,14 +377,19 @@ extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_
     DSSM_REQUIRE(B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
     const int cr = bn_chunk_rows(R, B);
     const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
-    DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)2 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
+    DSSM_REQUIRE(workspace && workspace_bytes >= ((size_t)3 * nt + 2) * L * sizeof(float), DSSM_ERR_WORKSPACE,
                  "dssm_bn_act_backward: workspace too small");
     float* part = (float*)workspace;
+    float* db_seg = db ? part + (size_t)3 * nt * L : nullptr;
     dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
     bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr);
     LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, B, R, gamma, rstd, dgamma, dbeta, db_seg);
     LAUNCH_CHECK("bn_bwd_finalize");
+    if (db) {
+        db_combine_kernel<<<cdiv(L, 128), 128, 0, st>>>(db_seg, L, db);
+        LAUNCH_CHECK("db_combine");
+    }
     bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift,
                                                                  dgamma, dbeta);
     LAUNCH_CHECK("bn_bwd_apply");

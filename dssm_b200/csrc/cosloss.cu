@@ -12,7 +12,8 @@ constexpr int CL_WARPS = 4;
 
 // dynamic smem per warp: 3*(1+NEG) floats (dot, dnorm, coefficient)
 __global__ void __launch_bounds__(CL_WARPS * 32)
-cos_softmax_loss_kernel(const float* __restrict__ Y, int B, int NEG, int L, float gamma, float loss_eps, float inv_denom,
+cos_softmax_loss_kernel(const float* __restrict__ Hin, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                        float* __restrict__ Y, int B, int NEG, int L, float gamma, float loss_eps, float inv_denom,
                         float* __restrict__ query_norm_single, float* __restrict__ doc_norm,
                         float* __restrict__ cos_sim_raw, float* __restrict__ cos_sim, float* __restrict__ prob,
                         float* __restrict__ loss_terms, float* __restrict__ dY) {
@@ -24,11 +25,25 @@ cos_softmax_loss_kernel(const float* __restrict__ Y, int B, int NEG, int L, floa
     float* s_c = s_dn + K1;
     const int j = blockIdx.x * CL_WARPS + w;
     if (j >= B) return;
+    if (Hin) {
+        // fused last-layer BN + activation (new_dssm.py:87,156-158): this warp owns the query row and the 1+NEG doc rows
+        // of group j, so it materialises their embeddings first; every lane later re-reads only what it wrote itself
+        for (int k = -1; k <= NEG; ++k) {
+            const size_t row = (k < 0) ? (size_t)j : (k == 0) ? (size_t)(B + j) : (size_t)(2 * B) + (size_t)j * NEG + (k - 1);
+            const int o = (k < 0) ? 0 : L;
+            for (int c = lane; c < L; c += 32) {
+                float x = __ldg(Hin + row * L + c);
+                if (scale) x = fmaf(x, __ldg(scale + o + c), __ldg(shift + o + c));
+                Y[row * L + c] = act_fwd(x, act);
+            }
+        }
+        __syncwarp();
+    }
     const float* q = Y + (size_t)j * L;
     // ||q||
     float qq = 0.f;
     for (int c = lane; c < L; c += 32) {
-        const float x = __ldg(q + c);
+        const float x = q[c];
         qq = fmaf(x, x, qq);
     }
     qq = warp_sum(qq);
@@ -39,9 +54,9 @@ cos_softmax_loss_kernel(const float* __restrict__ Y, int B, int NEG, int L, floa
         const float* d = Y + drow * L;
         float dd = 0.f, dq = 0.f;
         for (int c = lane; c < L; c += 32) {
-            const float x = __ldg(d + c);
+            const float x = d[c];
             dd = fmaf(x, x, dd);
-            dq = fmaf(x, __ldg(q + c), dq);
+            dq = fmaf(x, q[c], dq);
         }
         dd = warp_sum(dd);
         dq = warp_sum(dq);
@@ -100,11 +115,11 @@ cos_softmax_loss_kernel(const float* __restrict__ Y, int B, int NEG, int L, floa
     // dq = sum_k c_k/(qn*dn_k) * d_k - (sum_k c_k raw_k)/qn^2 * q ;  dd_k = c_k/(qn*dn_k) * q - c_k raw_k/dn_k^2 * d_k
     const float qcoef = sum_c_raw / (qn * qn);
     for (int c = lane; c < L; c += 32) {
-        const float qv = __ldg(q + c);
+        const float qv = q[c];
         float dqv = 0.f;
         for (int k = 0; k < K1; ++k) {
             const size_t drow = (k == 0) ? (size_t)(B + j) : (size_t)(2 * B) + (size_t)j * NEG + (k - 1);
-            const float dv = __ldg(Y + drow * L + c);
+            const float dv = Y[drow * L + c];
             const float ck = s_c[k], dn = s_dn[k];
             const float inv_qd = 1.f / (qn * dn);
             const float raw = s_dot[k] * inv_qd;
@@ -164,17 +179,17 @@ __global__ void merge_negative_doc_index_kernel(int B, int NEG, int* __restrict_
 
 using namespace dssm;
 
-extern "C" int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int32_t L, float gamma, float loss_eps,
-                                     int32_t loss_div_bs, float* query_norm_single, float* doc_norm, float* cos_sim_raw,
-                                     float* cos_sim, float* prob, float* loss_terms, float* loss, float* dY,
-                                     dssm_stream_t stream) {
+static int cos_softmax_loss_impl(const float* Hin, const float* scale, const float* shift, int act, float* Y, int32_t B, int32_t NEG,
+                                 int32_t L, float gamma, float loss_eps, int32_t loss_div_bs, float* query_norm_single,
+                                 float* doc_norm, float* cos_sim_raw, float* cos_sim, float* prob, float* loss_terms, float* loss,
+                                 float* dY, dssm_stream_t stream) {
     DSSM_REQUIRE(Y && loss_terms, DSSM_ERR_BAD_ARG, "dssm_cos_softmax_loss: null pointer");
     DSSM_REQUIRE(B > 0 && NEG > 0 && L > 0, DSSM_ERR_BAD_SHAPE, "dssm_cos_softmax_loss: bad shape B=%d NEG=%d L=%d", B, NEG, L);
     const size_t smem = (size_t)CL_WARPS * 3 * (NEG + 1) * sizeof(float);
     DSSM_REQUIRE(smem <= 48 * 1024, DSSM_ERR_BAD_SHAPE, "dssm_cos_softmax_loss: NEG=%d too large", NEG);
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_denom = loss_div_bs ? 1.0f / (float)B : 1.0f;
-    cos_softmax_loss_kernel<<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(Y, B, NEG, L, gamma, loss_eps, inv_denom,
+    cos_softmax_loss_kernel<<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(Hin, scale, shift, act, Y, B, NEG, L, gamma, loss_eps, inv_denom,
                                                                             query_norm_single, doc_norm, cos_sim_raw,
                                                                             cos_sim, prob, loss_terms, dY);
     LAUNCH_CHECK("cos_softmax_loss");
@@ -183,6 +198,26 @@ extern "C" int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int
         LAUNCH_CHECK("loss_reduce");
     }
     return DSSM_OK;
+}
+
+extern "C" int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int32_t L, float gamma, float loss_eps,
+                                     int32_t loss_div_bs, float* query_norm_single, float* doc_norm, float* cos_sim_raw,
+                                     float* cos_sim, float* prob, float* loss_terms, float* loss, float* dY,
+                                     dssm_stream_t stream) {
+    return cos_softmax_loss_impl(nullptr, nullptr, nullptr, DSSM_ACT_NONE, const_cast<float*>(Y), B, NEG, L, gamma, loss_eps, loss_div_bs,
+                                 query_norm_single, doc_norm, cos_sim_raw, cos_sim, prob, loss_terms, loss, dY, stream);
+}
+
+// Same, with the last layer's BN + activation fused in front: reads the pre-BN activations H [R,L] and the [2][L]
+// scale/shift (NULL = identity), WRITES the embeddings Y, then proceeds as above.
+extern "C" int dssm_cos_softmax_loss_fused(const float* H, const float* scale, const float* shift, int32_t act, float* Y, int32_t B,
+                                           int32_t NEG, int32_t L, float gamma, float loss_eps, int32_t loss_div_bs,
+                                           float* query_norm_single, float* doc_norm, float* cos_sim_raw, float* cos_sim,
+                                           float* prob, float* loss_terms, float* loss, float* dY, dssm_stream_t stream) {
+    DSSM_REQUIRE(H, DSSM_ERR_BAD_ARG, "dssm_cos_softmax_loss_fused: null pointer");
+    DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_cos_softmax_loss_fused: scale/shift must both be set or both NULL");
+    return cos_softmax_loss_impl(H, scale, shift, act, Y, B, NEG, L, gamma, loss_eps, loss_div_bs, query_norm_single, doc_norm,
+                                 cos_sim_raw, cos_sim, prob, loss_terms, loss, dY, stream);
 }
 
 extern "C" int dssm_merge_negative_doc(const float* doc_positive_y, const float* doc_negative_y, int32_t B, int32_t NEG,

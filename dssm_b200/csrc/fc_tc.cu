@@ -479,6 +479,22 @@ static int build_image(const float* src, int N, int K, int ld, int transposed, c
     return DSSM_OK;
 }
 
+// image of W for the forward (transposed = 1: B = W^T) or for dX (transposed = 0: B = W); internal, used by the tower to
+// build all images of a step beside the forward
+extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx) { return for_dx ? image_bytes(K, N) : image_bytes(N, K); }
+extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, void* img, dssm_stream_t stream) {
+    return for_dx ? build_image(W, K, N, N, 0, (char*)img, (cudaStream_t)stream) : build_image(W, N, K, N, 1, (char*)img, (cudaStream_t)stream);
+}
+extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, dssm_stream_t stream) {
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)img};
+    return tc::launch(a, (cudaStream_t)stream);
+}
+extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, dssm_stream_t stream) {
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)img};
+    return tc::launch(a, (cudaStream_t)stream);
+}
+
 // forward on the tensor cores: B = W^T as a pre-split swizzled image in `workspace`
 extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                               int32_t act, const float* W, const float* bias, int32_t N, float* Hout, void* workspace,

@@ -19,6 +19,15 @@ static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
 
 extern thread_local cudaEvent_t g_spmm_bwd_mid_event;
 
+}  // namespace dssm
+// tensor-core dense path with prebuilt weight images (fc_tc.cu)
+extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx);
+extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, void* img, dssm_stream_t stream);
+extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
+                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, dssm_stream_t stream);
+extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, dssm_stream_t stream);
+namespace dssm {
+
 // phase boundaries of one profiled step (dssm_tower_profile_step)
 enum { PH_START = 0, PH_SPMM_FWD, PH_DENSE_FWD, PH_COSLOSS, PH_DENSE_BWD, PH_CSC_BUILD, PH_DW_GATHER, PH_B1, PH_ADAM, PH_COUNT };
 struct PhaseTimer {
@@ -58,6 +67,10 @@ struct dssm_tower {
     float *bn_mean[DSSM_MAX_LAYERS + 1], *bn_var[DSSM_MAX_LAYERS + 1], *bn_rstd[DSSM_MAX_LAYERS + 1],
         *bn_scale[DSSM_MAX_LAYERS + 1], *bn_shift[DSSM_MAX_LAYERS + 1];
     float *Y, *qnorm, *dnorm, *cos_raw, *cos_sim, *prob, *loss_terms, *loss;
+    void* img_fwd[DSSM_MAX_LAYERS + 1];  // pre-split weight images of layer l (tensor-core mode), rebuilt every step
+    void* img_dx[DSSM_MAX_LAYERS + 1];
+    cudaEvent_t ev_img;
+    bool img_forked;
     void *bn_ws, *dw_ws, *sp_ws, *fc_ws;
     size_t bn_ws_bytes, dw_ws_bytes, sp_ws_bytes, fc_ws_bytes;
     // last forward's CSR (backward reuses it)
@@ -152,6 +165,13 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     }
     t->fc_ws_bytes = fcw;
     t->fc_ws = a.take<char>(fcw ? fcw : 256);
+    for (int l = 2; l <= n; ++l) {
+        t->img_fwd[l] = t->img_dx[l] = nullptr;
+        if (t->cfg.gemm_mode == DSSM_GEMM_TC_3XTF32) {
+            t->img_fwd[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 0));
+            t->img_dx[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 1));
+        }
+    }
     t->sp_ws_bytes = dssm_spmm_bwd_dw_workspace_bytes(R, t->D, t->L[1], max_nnz);
     t->sp_ws = a.take<char>(t->sp_ws_bytes);
     return a.off;
@@ -209,7 +229,9 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->side = nullptr;
     t->ev_fork = nullptr;
     t->ev_join = nullptr;
+    t->ev_img = nullptr;
     t->csc_forked = false;
+    t->img_forked = false;
     t->launches = 0;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
@@ -224,6 +246,7 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (t->graph_dp) cudaGraphDestroy(t->graph_dp);
     if (t->ev_fork) cudaEventDestroy(t->ev_fork);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->ev_img) cudaEventDestroy(t->ev_img);
     if (t->side) cudaStreamDestroy(t->side);
     delete t;
 }
@@ -241,6 +264,7 @@ extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nn
     tmp.side = nullptr;
     tmp.ev_fork = nullptr;
     tmp.ev_join = nullptr;
+    tmp.ev_img = nullptr;
     return tower_carve(&tmp, nullptr, max_nnz);
 }
 
@@ -291,6 +315,7 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
         CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_img, cudaEventDisableTiming));
     }
     t->csc_forked = false;
     t->bound = true;
@@ -310,11 +335,34 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     const int n = t->n_layers, R = t->R, B = t->B;
     mark(PH_START);
     t->csc_forked = false;
-    if (want_grad && on_train && t->L[1] % 4 == 0 && t->L[1] <= 1024 && !(g_timer && g_timer->on)) {
-        // fork: CSC build on the side stream, concurrent with the whole forward and the dense backward
-        cudaStream_t main_st = (cudaStream_t)s;
+    t->img_forked = false;
+    const bool tc = c.gemm_mode == DSSM_GEMM_TC_3XTF32 && n >= 2;
+    const bool timing = g_timer && g_timer->on;
+    const bool train = want_grad && on_train;
+    const bool fork_csc = train && t->L[1] % 4 == 0 && t->L[1] <= 1024 && !timing;
+    cudaStream_t main_st = (cudaStream_t)s;
+    // Side stream, forked here and joined where its results are consumed: (1) the pre-split weight images of the
+    // tensor-core dense layers (they depend on the parameters only), (2) the per-batch CSC of X for the dW1 gather
+    // (it depends on the batch only).  Both run beside the FC1 SpMM / the dense stack.
+    cudaStream_t aux = timing ? main_st : t->side;
+    if (!timing && (tc || fork_csc)) {
         CUDA_TRY(cudaEventRecord(t->ev_fork, main_st));
         CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
+    }
+    auto build_images = [&]() -> int {
+        for (int l = 2; l <= n; ++l) {
+            const std::string ls = std::to_string(l);
+            TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 0, t->img_fwd[l], (dssm_stream_t)aux));
+            if (train) TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 1, t->img_dx[l], (dssm_stream_t)aux));
+        }
+        return DSSM_OK;
+    };
+    if (tc && !timing) {
+        TRY(build_images());
+        CUDA_TRY(cudaEventRecord(t->ev_img, t->side));
+        t->img_forked = true;
+    }
+    if (fork_csc) {
         TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1], t->grads_p ? t->G_("W1") : nullptr, t->sp_ws,
                                     t->sp_ws_bytes, (dssm_stream_t)t->side));
         CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
@@ -322,6 +370,8 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     }
     TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
     mark(PH_SPMM_FWD);
+    if (tc && timing) TRY(build_images());  // profiled step: serial, accounted to the dense forward
+    if (t->img_forked) CUDA_TRY(cudaStreamWaitEvent(main_st, t->ev_img, 0));
     for (int l = 1; l <= n; ++l) {
         const std::string ls = std::to_string(l);
         if (c.use_bn) {
@@ -334,16 +384,22 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         const float* sh = c.use_bn ? t->bn_shift[l] : nullptr;
         if (l < n) {
             const std::string ns = std::to_string(l + 1);
-            TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
-                            t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));
+            if (tc && t->L[l] % 4 == 0 && t->L[l + 1] % 4 == 0) {
+                TRY(dssm_fc_fwd_tc_img(t->h[l], R, t->L[l], B, sc, sh, c.act, t->img_fwd[l + 1], t->P_("b" + ns), t->L[l + 1],
+                                       t->h[l + 1], s));
+            } else {
+                TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
+                                t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));
+            }
         } else {
-            TRY(dssm_bn_act_apply(t->h[l], R, t->L[l], B, sc, sh, c.act, t->Y, s));
+            mark(PH_DENSE_FWD);
+            // last layer: BN + activation fused into the cosine / loss kernel, which also writes the embeddings Y
+            TRY(dssm_cos_softmax_loss_fused(t->h[l], sc, sh, c.act, t->Y, B, t->NEG, t->L[n], c.gamma, c.loss_eps, c.loss_div_bs,
+                                            t->qnorm, t->dnorm, t->cos_raw, t->cos_sim, t->prob, t->loss_terms, t->loss,
+                                            want_grad ? t->dh[n] : nullptr, s));
+            mark(PH_COSLOSS);
         }
     }
-    mark(PH_DENSE_FWD);
-    TRY(dssm_cos_softmax_loss(t->Y, B, t->NEG, t->L[n], c.gamma, c.loss_eps, c.loss_div_bs, t->qnorm, t->dnorm,
-                              t->cos_raw, t->cos_sim, t->prob, t->loss_terms, t->loss, want_grad ? t->dh[n] : nullptr, s));
-    mark(PH_COSLOSS);
     t->cur_indptr = indptr; t->cur_indices = indices; t->cur_values = values;
     t->fwd_train_done = want_grad && on_train;
     return DSSM_OK;
@@ -364,18 +420,23 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
         if (c.use_bn) {
             TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, t->P_("bn" + ls + "_gamma"), t->bn_mean[l],
                                      t->bn_rstd[l], t->bn_scale[l], t->bn_shift[l], t->G_("bn" + ls + "_gamma"),
-                                     t->G_("bn" + ls + "_beta"), t->bn_ws, t->bn_ws_bytes, s));
+                                     t->G_("bn" + ls + "_beta"), t->G_("b" + ls), t->bn_ws, t->bn_ws_bytes, s));
         } else {
             TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                     nullptr, nullptr, nullptr, 0, s));
+                                     nullptr, nullptr, nullptr, nullptr, 0, s));
         }
         if (l > 1) {
             const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
             const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
+            // under BN the bias gradient came out of dssm_bn_act_backward; without BN it is the column sum of dH
             TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
-                               t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
-            TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, t->fc_ws,
-                               t->fc_ws_bytes, s));
+                               c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
+            if (c.gemm_mode == DSSM_GEMM_TC_3XTF32 && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
+                TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], s));
+            } else {
+                TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, t->fc_ws,
+                                   t->fc_ws_bytes, s));
+            }
         } else {
             mark(PH_DENSE_BWD);
             if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
@@ -395,7 +456,7 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
                 TRY(rc);
             }
             mark(PH_DW_GATHER);
-            TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
+            if (!c.use_bn) TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
             mark(PH_B1);
         }
     }

@@ -190,18 +190,20 @@ def batch_normalization(x, phase_train: bool, out_size: int, state: Optional[BNS
     return bn_act_apply(x, state.scale, state.shift, None, B), state
 
 
-def bn_act_backward(dA, H, B: int, act, state: Optional[BNState]):
-    """In place: dA becomes dLoss/dH.  Returns (dgamma, dbeta) [2,L] (None without BN)."""
+def bn_act_backward(dA, H, B: int, act, state: Optional[BNState], want_db: bool = False):
+    """In place: dA becomes dLoss/dH.  Returns (dgamma, dbeta) [2,L] (None without BN), plus db [L] when want_db."""
     R, L = H.shape
     if state is None:
-        check(lib.dssm_bn_act_backward(ptr(dA), ptr(H), R, L, B, ACT[act], None, None, None, None, None, None, None, None, 0,
-                                       stream_ptr()))
-        return None, None
+        check(lib.dssm_bn_act_backward(ptr(dA), ptr(H), R, L, B, ACT[act], None, None, None, None, None, None, None, None, None,
+                                       0, stream_ptr()))
+        return (None, None, None) if want_db else (None, None)
     dgamma, dbeta = _f32((2, L), H.device), _f32((2, L), H.device)
+    db = _f32((L,), H.device) if want_db else None
     ws = _ws(lib.dssm_bn_workspace_bytes(R, L), H.device)
     check(lib.dssm_bn_act_backward(ptr(dA), ptr(H), R, L, B, ACT[act], ptr(state.gamma), ptr(state.mean), ptr(state.rstd),
-                                   ptr(state.scale), ptr(state.shift), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), stream_ptr()))
-    return dgamma, dbeta
+                                   ptr(state.scale), ptr(state.shift), ptr(dgamma), ptr(dbeta), ptr(db), ptr(ws), ws.numel(),
+                                   stream_ptr()))
+    return (dgamma, dbeta, db) if want_db else (dgamma, dbeta)
 
 
 # ---- Merge_Negative_Doc / Cosine_Similarity / Loss -----------------------------------------------------

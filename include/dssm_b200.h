@@ -135,11 +135,14 @@ int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B, const flo
                       int32_t act, float* Y, dssm_stream_t stream);
 
 /* Backward of act(BN(x)) for one layer.  In: dA = dLoss/d(post-activation) [R,L] ; H = pre-BN
- * activations saved by the forward.  Out (in place over dA): dH = dLoss/dH; dgamma,dbeta [2][L].
- * With scale == NULL (no-BN mode) only the activation derivative is applied. */
+ * activations saved by the forward.  Out (in place over dA): dH = dLoss/dH; dgamma,dbeta [2][L]; optionally
+ * db [L] = sum_r dH[r,:] (the gradient of the pre-BN bias), evaluated through the exact identity
+ * sum_r dH = -gamma*rstd*dgamma*mean(xhat) per instance -- analytically zero, numerically rounding noise, exactly as
+ * the column sum the reference takes.  With scale == NULL (no-BN mode) only the activation derivative is applied
+ * (db is not written: use dssm_colsum). */
 int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act,
                          const float* gamma, const float* mean, const float* rstd, const float* scale,
-                         const float* shift, float* dgamma, float* dbeta, void* workspace,
+                         const float* shift, float* dgamma, float* dbeta, float* db, void* workspace,
                          size_t workspace_bytes, dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -192,6 +195,13 @@ int dssm_cos_softmax_loss(const float* Y, int32_t B, int32_t NEG, int32_t L, flo
                           int32_t loss_div_bs, float* query_norm_single, float* doc_norm, float* cos_sim_raw,
                           float* cos_sim, float* prob, float* loss_terms, float* loss, float* dY,
                           dssm_stream_t stream);
+
+/* Same with the last layer's BN + activation (new_dssm.py:87,156-158) fused in front: reads the pre-BN activations
+ * H [R,L] and the [2][L] scale/shift (NULL = identity), WRITES the embeddings Y [R,L], then proceeds as above. */
+int dssm_cos_softmax_loss_fused(const float* H, const float* scale, const float* shift, int32_t act, float* Y, int32_t B,
+                                int32_t NEG, int32_t L, float gamma, float loss_eps, int32_t loss_div_bs,
+                                float* query_norm_single, float* doc_norm, float* cos_sim_raw, float* cos_sim, float* prob,
+                                float* loss_terms, float* loss, float* dY, dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training (new_dssm.py:215-217): tf.train.AdamOptimizer over one flat parameter buffer.
