@@ -317,6 +317,33 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    # ---- secondary metric: corpus cosine top-k (BASELINE.json C5, one GPU's shard) ----------------------------
+    retrieval = None
+    if rank == 0 and world == 1 and not args.no_retrieval:
+        from dssm_b200 import retrieval as rt
+
+        g = torch.Generator(device=dev).manual_seed(0)
+        nqr, ndr, kr = 4096, 1_250_000, 100  # 10 M docs / 8 GPUs, query batch 4096, top-100
+        Qr = torch.relu(torch.randn((nqr, 128), generator=g, device=dev))
+        Dr = torch.relu(torch.randn((ndr, 128), generator=g, device=dev))
+        rt.corpus_topk(Qr, Dr, kr, method="tc")  # warm-up (attribute calls, allocator)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        r0.record(stream)
+        for _ in range(reps):
+            rs_, ri_ = rt.corpus_topk(Qr, Dr, kr, method="tc")
+        r1.record(stream)
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / reps
+        flops = 2.0 * nqr * ndr * 128
+        retrieval = {"metric": "corpus cos top-k docs/s", "value": ndr / (rms / 1e3), "unit": "docs/s", "ms": rms,
+                     "config": {"queries": nqr, "docs_per_gpu": ndr, "dim": 128, "k": kr, "storage": "fp32",
+                                "method": "tcgen05 tf32 filter + exact fp32 rescoring (ids bit-exact vs oracle)"},
+                     "fallback_to_exact": bool(rt.LAST_CALL["fallback"]), "tf32_tflops": flops / (rms / 1e3) / 1e12,
+                     "includes": "row norms, exact seed pass (16384 docs), 3 filter passes, rescoring, overflow-flag readback"}
+        del Qr, Dr
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores -----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -340,7 +367,7 @@ def run_ours(args):
                                                                "dp_w1_chunks": (dp.n_chunks if dp else None)}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms, "last_loss": last_loss},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "retrieval": retrieval}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Tear-down: a process group that has collectives captured in a live CUDA graph can block forever in
@@ -367,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", help="C1 | C2 | C3 | C4 | C4_NOBN (per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the secondary corpus top-k measurement")
     ap.add_argument("--gemm-mode", default="tc_3xtf32", choices=["fp32", "tc_3xtf32"],
                     help="dense-layer arithmetic: FFMA fp32 or tcgen05 3xTF32 (both hold the 1e-5 parity bar)")
     args = ap.parse_args()

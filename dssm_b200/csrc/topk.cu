@@ -203,6 +203,22 @@ static TopkWs carve_topk(void* ws, int nq, int64_t nd, int k) {
     return w;
 }
 
+// host helpers shared with the tensor-core path (topk_tc.cu)
+int topk_row_norms(const float* X, int64_t n, int d, float* out, cudaStream_t st) {
+    row_norm_seq_kernel<<<cdiv(n, 128), 128, 0, st>>>(X, n, d, out);
+    LAUNCH_CHECK("row_norm_seq");
+    return DSSM_OK;
+}
+int topk_exact_chunk(const float* Q, int nq, const float* docs, int64_t doc0, int cd, int d, const float* qn, const float* dn, float* S,
+                     int ldS, int id0, int k, float* run_s, int* run_i, int* run_cnt, cudaStream_t st) {
+    dim3 grid(cdiv(cd, TK_DT), cdiv(nq, TK_QT));
+    exact_scores_kernel<<<grid, 256, 0, st>>>(Q, nq, docs, doc0, cd, d, qn, dn, S, ldS);
+    LAUNCH_CHECK("exact_scores");
+    chunk_select_kernel<<<cdiv(nq, 4), 128, (size_t)4 * 2 * k * sizeof(float), st>>>(S, ldS, nq, cd, id0, k, run_s, run_i, run_cnt);
+    LAUNCH_CHECK("chunk_select");
+    return DSSM_OK;
+}
+
 }  // namespace dssm
 
 using namespace dssm;

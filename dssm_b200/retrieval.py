@@ -14,13 +14,35 @@ import torch.distributed as dist
 from ._lib import check, lib, ptr, stream_ptr
 
 
-def corpus_topk(Q: torch.Tensor, docs: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(scores [nq,k] fp32, ids [nq,k] int32), sorted; ids = id_offset + local row."""
+LAST_CALL = {"method": None, "fallback": False}  # what the most recent corpus_topk did (tests / bench read it)
+TC_MIN_DOCS = 32768  # below this the exact kernels are as fast as the filter + rescore pipeline
+
+
+def corpus_topk(Q: torch.Tensor, docs: torch.Tensor, k: int, id_offset: int = 0, method: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores [nq,k] fp32, ids [nq,k] int32), sorted; ids = id_offset + local row.
+    method: "exact" (SIMT, the oracle's arithmetic for every pair), "tc" (tcgen05 tf32 filter + exact rescoring of the
+    survivors; same ids and scores bit for bit; needs d == 128), "auto" (tc when it applies and the corpus is large)."""
     if not (Q.is_cuda and docs.is_cuda):
         raise ValueError("corpus_topk takes CUDA tensors (there is no CPU path)")
     nq, d = Q.shape
     nd = docs.shape[0]
     k = min(k, nd)
+    if method == "auto":
+        method = "tc" if (d == 128 and nd >= TC_MIN_DOCS) else "exact"
+    if method == "tc":
+        nb = lib.dssm_corpus_topk_tc_workspace_bytes(nq, nd, d, k)
+        ws = torch.empty(nb, dtype=torch.uint8, device=Q.device)
+        s = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        i = torch.empty((nq, k), dtype=torch.int32, device=Q.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=Q.device)
+        check(lib.dssm_corpus_topk_tc(ptr(Q), nq, ptr(docs), nd, d, k, id_offset, ptr(s), ptr(i), ptr(flag), ptr(ws), nb, stream_ptr()))
+        fell_back = int(flag.item()) != 0
+        LAST_CALL.update(method="tc", fallback=fell_back)
+        if not fell_back:
+            return s, i
+        # a candidate list overflowed (thresholds too loose for this data): the exact kernels always work
+    else:
+        LAST_CALL.update(method="exact", fallback=False)
     nb = lib.dssm_corpus_topk_workspace_bytes(nq, nd, d, k)
     ws = torch.empty(nb, dtype=torch.uint8, device=Q.device)
     s = torch.empty((nq, k), dtype=torch.float32, device=Q.device)

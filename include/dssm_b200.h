@@ -226,6 +226,14 @@ size_t dssm_corpus_topk_workspace_bytes(int32_t nq, int64_t nd, int32_t d, int32
 int dssm_corpus_topk(const float* Q, int32_t nq, const float* docs, int64_t nd, int32_t d, int32_t k,
                      int32_t id_offset, float* out_scores, int32_t* out_ids, void* workspace,
                      size_t workspace_bytes, dssm_stream_t stream);
+/* Tensor-core path of the same contract (d must be 128): tcgen05 tf32 contraction with a per-query threshold filter in
+ * the TMEM epilogue, then exact fp32 rescoring of the survivors, so ids and scores are bit-identical to
+ * dssm_corpus_topk.  *overflow_flag (device int) becomes 1 if a candidate list overflowed -- the result is then
+ * incomplete and the caller must rerun dssm_corpus_topk (dssm_b200/retrieval.py does). */
+size_t dssm_corpus_topk_tc_workspace_bytes(int32_t nq, int64_t nd, int32_t d, int32_t k);
+int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs, int64_t nd, int32_t d, int32_t k, int32_t id_offset,
+                        float* out_scores, int32_t* out_ids, int32_t* overflow_flag, void* workspace, size_t workspace_bytes,
+                        dssm_stream_t stream);
 int dssm_topk_merge(const float* part_scores, const int32_t* part_ids, int32_t n_parts, int32_t nq, int32_t k,
                     float* out_scores, int32_t* out_ids, dssm_stream_t stream);
 

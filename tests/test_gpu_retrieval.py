@@ -46,3 +46,45 @@ def test_topk_merge_equals_whole_corpus():
     assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy(), rs)
     ws, wi = corpus_topk(Qd, Dd, 100)
     assert torch.equal(wi, i) and torch.equal(ws, s)
+
+
+@pytest.mark.parametrize("nq,nd,k", [(64, 40000, 100), (130, 70001, 10)])
+def test_topk_tensor_core_filter_bit_exact_vs_oracle(nq, nd, k):
+    """tcgen05 tf32 filter + exact rescoring returns the oracle's ids and scores bit for bit (ties, zero rows, a doc
+    range that is not a multiple of the 128-doc tile)."""
+    from dssm_b200 import corpus_topk
+    from oracle import corpus_topk_oracle
+
+    Q, D = make(nq, nd, 128, nq + nd)
+    D[nd - 5] = D[3]  # duplicate far apart (one in the exact seed pass, one in the tensor-core pass)
+    D[30000] = D[20000]
+    D[17000] = 0  # zero-norm doc in the tensor-core range
+    Q[1] = Q[0]
+    from dssm_b200 import retrieval
+
+    s, i = corpus_topk(torch.from_numpy(Q).cuda(), torch.from_numpy(D).cuda(), k, id_offset=7, method="tc")
+    assert retrieval.LAST_CALL == {"method": "tc", "fallback": False}  # the tensor-core path itself produced this
+    rs, ri = corpus_topk_oracle(Q, D, k, id_offset=7)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(s.cpu().numpy(), rs)
+
+
+def test_topk_tensor_core_equals_exact_path_large():
+    """300k docs, several filter passes with growing chunks: same result as the all-pairs exact kernels."""
+    from dssm_b200 import corpus_topk
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Q = torch.relu(torch.randn((256, 128), generator=g, device="cuda"))
+    D = torch.relu(torch.randn((300000, 128), generator=g, device="cuda"))
+    s1, i1 = corpus_topk(Q, D, 100, method="exact")
+    from dssm_b200 import retrieval
+
+    s2, i2 = corpus_topk(Q, D, 100, method="tc")
+    assert retrieval.LAST_CALL == {"method": "tc", "fallback": False}
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    # signed (not post-relu) embeddings: thresholds stay positive at the top of the ranking, the filter still applies
+    Qs, Ds = torch.randn((128, 128), generator=g, device="cuda"), torch.randn((100000, 128), generator=g, device="cuda")
+    s3, i3 = corpus_topk(Qs, Ds, 50, method="exact")
+    s4, i4 = corpus_topk(Qs, Ds, 50, method="tc")
+    assert retrieval.LAST_CALL["method"] == "tc"  # may fall back on signed data; the result must be right either way
+    assert torch.equal(i3, i4) and torch.equal(s3, s4)
