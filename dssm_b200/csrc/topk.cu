@@ -17,13 +17,27 @@ namespace dssm {
 constexpr int TK_QT = 64, TK_DT = 64, TK_TT = 32;
 constexpr int TK_CHUNK = 16384;  // docs per chunk
 
-__global__ void row_norm_seq_kernel(const float* __restrict__ X, int64_t n, int d, float* __restrict__ out) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const float* x = X + r * d;
+// ||x|| with the oracle's strictly sequential fp32 sum of squares.  128 rows per block: 128 x 32 column slabs are
+// staged through shared memory (coalesced 128-byte row segments in, conflict-free column walks out, stride 33), and
+// thread r accumulates row r in t order across the slabs.
+__global__ void __launch_bounds__(128) row_norm_seq_kernel(const float* __restrict__ X, int64_t n, int d, float* __restrict__ out) {
+    __shared__ float slab[128][33];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * 128;
     float acc = 0.f;
-    for (int t = 0; t < d; ++t) acc = __fadd_rn(acc, __fmul_rn(x[t], x[t]));
-    out[r] = __fsqrt_rn(acc);
+    for (int c0 = 0; c0 < d; c0 += 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {  // 4096 elements / 128 threads, column fastest
+            const int e = tid + i * 128;
+            const int rr = e >> 5, cc = e & 31;
+            slab[rr][cc] = (r0 + rr < n && c0 + cc < d) ? __ldg(X + (r0 + rr) * d + c0 + cc) : 0.f;
+        }
+        __syncthreads();
+        const int cmax = min(32, d - c0);
+        for (int t = 0; t < cmax; ++t) acc = __fadd_rn(acc, __fmul_rn(slab[tid][t], slab[tid][t]));
+        __syncthreads();
+    }
+    if (r0 + tid < n) out[r0 + tid] = __fsqrt_rn(acc);
 }
 
 // S[q, j] = key(score(q, doc0 + j)) for j < cd

@@ -32,35 +32,50 @@ constexpr int TILE_BYTES = QT * DIM * 4;     // 64 KB
 constexpr int KBLK_BYTES = QT * 128;         // one [128 rows x 32 floats] block
 constexpr int CAP = 2048;                    // candidate ids per query per pass
 constexpr float MARGIN = 2.5e-3f;            // > 2^-9 (tf32 truncation of both operands) + fp32 slack
-constexpr int SEED_DOCS = 16384;
+constexpr int SEED_DOCS = 4096;              // exact pass that seeds the thresholds; later passes grow x4
 
-// stage one [128 x 128] fp32 tile (rows row0.. of X, `rows_valid` of them real) into SW128 K-major blocks with cp.async
-__device__ __forceinline__ void load_tile_async(char* smem_tile, const float* __restrict__ X, int64_t row0, int rows_valid, int tid) {
+// stage one [128 x 128] fp32 tile (rows row0.. of X, `rows_valid` of them real) into SW128 K-major blocks with cp.async.
+// Chunk i of a thread always goes to the same place of the tile: 16-byte chunk id = tid + 256*i  ->  row id/32,
+// k-block (id%32)/8, chunk-in-row id%8 (consecutive threads read consecutive 16 B of a 512-byte row).
+__device__ __forceinline__ uint32_t tile_dst_off(int id) {
+    const int r = id >> 5, cc = id & 31;
+    return (uint32_t)((cc >> 3) * KBLK_BYTES + r * 128 + (((cc & 7) ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void load_tile_async(uint32_t smem_tile, const float* __restrict__ X, int64_t row0, int rows_valid, int tid) {
+    const float* src0 = X + row0 * DIM + (size_t)tid * 4;  // chunk id -> element offset id*4 (row-major tile is contiguous)
+    if (rows_valid >= QT) {
 #pragma unroll
-    for (int i = 0; i < (QT * DIM / 4) / THREADS; ++i) {  // 4096 16-byte chunks / 256 threads
-        const int id = tid + i * THREADS;
-        const int r = id >> 5, cc = id & 31;  // 32 chunks per row: consecutive threads read consecutive 16 B
-        const int kb = cc >> 3, c = cc & 7;
-        const uint32_t dst = smem_u32(smem_tile + kb * KBLK_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
-        const float* src = X + (row0 + (r < rows_valid ? r : 0)) * DIM + cc * 4;
-        const int bytes = r < rows_valid ? 16 : 0;  // zero-fill rows past the end
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        for (int i = 0; i < (QT * DIM / 4) / THREADS; ++i) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_tile + tile_dst_off(tid + i * THREADS)),
+                         "l"(src0 + (size_t)i * THREADS * 4)
+                         : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (QT * DIM / 4) / THREADS; ++i) {
+            const int id = tid + i * THREADS;
+            const bool ok = (id >> 5) < rows_valid;  // zero-fill rows past the end
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_tile + tile_dst_off(id)),
+                         "l"(ok ? src0 + (size_t)i * THREADS * 4 : X), "r"(ok ? 16 : 0)
+                         : "memory");
+        }
     }
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
 topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ docs, int64_t doc_lo, int64_t doc_hi,
                       const float* __restrict__ dn, const float* __restrict__ tq /* (tau - margin) * ||q|| */,
-                      int id_base /* id of doc row 0 */, int* __restrict__ cand, int* __restrict__ cand_cnt,
+                      const float* __restrict__ qn, int id_base /* id of doc row 0 */, int2* __restrict__ cand, int* __restrict__ cand_cnt,
                       int* __restrict__ overflow, int tiles_per_split) {
     extern __shared__ char smem_raw[];
     __shared__ uint64_t mma_done[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_dn[2][DT];
+    __shared__ __align__(16) float s_dn[3][DT];  // doc norms of the tiles in flight (t-1 being drained, t in the MMA, t+1 loading)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    char* q_tile = smem;
-    char* d_tile[2] = {smem + TILE_BYTES, smem + 2 * TILE_BYTES};
+    const uint32_t q_tile = smem_u32(smem);
+    const uint32_t d_tile0 = q_tile + TILE_BYTES;  // stage s at d_tile0 + s * TILE_BYTES
+    float4* stash = reinterpret_cast<float4*>(smem + 3 * TILE_BYTES);  // [THREADS][8] float4, survivors' slow path
 
     const int q0 = blockIdx.x * QT;
     const int64_t n_docs = doc_hi - doc_lo;
@@ -79,7 +94,7 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
     load_tile_async(q_tile, Q, q0, min(QT, nq - q0), tid);
     {
         const int64_t d0 = doc_lo + (int64_t)t_begin * DT;
-        load_tile_async(d_tile[0], docs, d0, (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT), tid);
+        load_tile_async(d_tile0, docs, d0, (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT), tid);
         if (tid < DT) s_dn[0][tid] = (d0 + tid < doc_hi) ? __ldg(dn + d0 + tid) : 0.f;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -90,30 +105,59 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
     const uint32_t idesc = make_idesc_tf32(QT, DT);
 
     // this thread's query (TMEM lane) and its scaled threshold
-    const int lane_grp = warp & 3, half = warp >> 2;
+    const int lane_grp = warp & 3, half = warp >> 2;  // 8 warps: 4 TMEM lane groups x 2 column halves
     const int q = q0 + lane_grp * 32 + lane;
     const float t_q = q < nq ? __ldg(tq + q) : INFINITY;
+    const float inv_qn = q < nq ? 1.0f / __ldg(qn + q) : 0.f;
 
     // drain the accumulator of this CTA's tile number `tr` (relative index): approx dot -> threshold test -> append
+    auto wait_mma = [&](int tr) {
+        mbar_wait(&mma_done[tr & 1], (uint32_t)((tr >> 1) & 1));
+        tc_fence_after();
+    };
     auto drain = [&](int tr) {
         const int bb = tr & 1;
-        mbar_wait(&mma_done[bb], (uint32_t)((tr >> 1) & 1));
-        tc_fence_after();
+        const float4* nrm4 = reinterpret_cast<const float4*>(s_dn[tr % 3]);
         const int64_t d0 = doc_lo + (int64_t)(t_begin + tr) * DT;
+        const int nvalid = (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             uint32_t r[32];
             const int col0 = half * 64 + ch * 32;
             tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(bb * DT + col0), r);
+            // keep iff cos_approx >= tau - margin  <=>  dot >= (tau - margin) * ||q|| * ||d||  (norms >= 0).  Survivors
+            // are rare: collect the 32 verdicts in a bit mask, branch once.
+            uint32_t keep = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dot = __uint_as_float(r[j]);
-                const float nd = s_dn[bb][col0 + j];
-                // keep iff cos_approx >= tau - margin  <=>  dot >= (tau - margin) * ||q|| * ||d||   (norms are >= 0)
-                if (dot >= t_q * nd && d0 + col0 + j < doc_hi) {
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 nd = nrm4[(col0 >> 2) + j4];
+                keep |= (__uint_as_float(r[4 * j4 + 0]) >= t_q * nd.x ? 1u : 0u) << (4 * j4 + 0);
+                keep |= (__uint_as_float(r[4 * j4 + 1]) >= t_q * nd.y ? 1u : 0u) << (4 * j4 + 1);
+                keep |= (__uint_as_float(r[4 * j4 + 2]) >= t_q * nd.z ? 1u : 0u) << (4 * j4 + 2);
+                keep |= (__uint_as_float(r[4 * j4 + 3]) >= t_q * nd.w ? 1u : 0u) << (4 * j4 + 3);
+            }
+            if (nvalid - col0 < 32) keep &= (nvalid - col0 <= 0) ? 0u : (0xffffffffu >> (32 - (nvalid - col0)));  // partial last tile
+            if (keep) {
+                // this lane has survivors in the chunk: park its 32 dots in its own shared-memory row (XOR-swizzled
+                // float4 slots) so that the few survivors can be fetched by index without forcing r[] out of registers
+                float4* row = stash + (size_t)tid * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    row[i ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                      __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                const float* rowf = reinterpret_cast<const float*>(row);
+                while (keep) {
+                    const int j = __ffs(keep) - 1;
+                    keep &= keep - 1;
                     const int pos = atomicAdd(cand_cnt + q, 1);
-                    if (pos < CAP) cand[(size_t)q * CAP + pos] = id_base + (int)(d0 + col0 + j);
-                    else *overflow = 1;
+                    if (pos < CAP) {
+                        // id + the approximate cosine (the rescoring pass skips candidates that can no longer enter the list)
+                        const float dot = rowf[(((j >> 2) ^ (lane & 7)) << 2) + (j & 3)];
+                        const float nd = s_dn[tr % 3][col0 + j];
+                        cand[(size_t)q * CAP + pos] = make_int2(id_base + (int)(d0 + col0 + j), __float_as_int(dot * inv_qn / nd));
+                    } else {
+                        *overflow = 1;
+                    }
                 }
             }
         }
@@ -130,26 +174,28 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
             tc_fence_after();
 #pragma unroll
             for (int kb = 0; kb < KBLKS; ++kb) {
-                const uint64_t da = make_desc_k_sw128(smem_u32(q_tile + kb * KBLK_BYTES));
-                const uint64_t db = make_desc_k_sw128(smem_u32(d_tile[b] + kb * KBLK_BYTES));
+                const uint64_t da = make_desc_k_sw128(q_tile + kb * KBLK_BYTES);
+                const uint64_t db = make_desc_k_sw128(d_tile0 + b * TILE_BYTES + kb * KBLK_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                     mma_tf32(tmem_d + (uint32_t)(b * DT), da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
             }
             mma_commit(&mma_done[b]);
         }
-        // while the tensor core works on tile t: drain tile t-1 (its smem stage and accumulator become free) ...
-        if (t > t_begin) drain(t - 1 - t_begin);
-        __syncthreads();  // everyone is done with stage (t-1)&1 and its norms
-        // ... and prefetch tile t+1 into the stage tile t-1 used
+        // While the tensor core works on tile t: once MMA(t-1) has retired, its smem stage is free -> start the
+        // cp.async prefetch of tile t+1 into it FIRST, then drain accumulator t-1 (TMEM reads do not touch smem), so
+        // the copy overlaps the epilogue instead of being waited for right after it was issued.
+        const int tr = t - t_begin;
+        if (tr > 0) wait_mma(tr - 1);
         if (t + 1 < t_end) {
-            const int nb = b ^ 1;
             const int64_t d0 = doc_lo + (int64_t)(t + 1) * DT;
-            load_tile_async(d_tile[nb], docs, d0, (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT), tid);
-            if (tid < DT) s_dn[nb][tid] = (d0 + tid < doc_hi) ? __ldg(dn + d0 + tid) : 0.f;
+            load_tile_async(d_tile0 + (b ^ 1) * TILE_BYTES, docs, d0, (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT), tid);
+            if (tid < DT) s_dn[(tr + 1) % 3][tid] = (d0 + tid < doc_hi) ? __ldg(dn + d0 + tid) : 0.f;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tr > 0) drain(tr - 1);
     }
+    wait_mma(t_end - 1 - t_begin);
     drain(t_end - 1 - t_begin);  // last tile
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, 256);
@@ -159,7 +205,7 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
 // into the running top-k ordered by (score desc, id asc), new threshold, candidate counter reset.
 __global__ void __launch_bounds__(128)
 topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ docs /* row 0 = id id_base */, int id_base,
-                           int d, const float* __restrict__ qn, const float* __restrict__ dn, int k, const int* __restrict__ cand,
+                           int d, const float* __restrict__ qn, const float* __restrict__ dn, int k, const int2* __restrict__ cand,
                            int* __restrict__ cand_cnt, float* __restrict__ run_s, int* __restrict__ run_i,
                            int* __restrict__ run_cnt, float* __restrict__ tq) {
     extern __shared__ float sm[];
@@ -175,21 +221,48 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
     }
     __syncwarp();
     const int n = min(cand_cnt[q], CAP);
-    const float* qrow = Q + (size_t)q * d;
     const float nqv = qn[q];
+    // per-warp staging: the query row and 32 candidate rows (row stride d+1 words: conflict-free column walks), so the
+    // global reads are coalesced 512-byte rows while every lane still sums ITS candidate strictly in t order
+    float* sq = reinterpret_cast<float*>(sm + (size_t)4 * 2 * k) + (size_t)w * (33 * (d + 1));
+    float* srow = sq + (d + 1);
+    for (int t = lane; t < d; t += 32) sq[t] = __ldg(Q + (size_t)q * d + t);
+    __syncwarp();
     for (int base = 0; base < n; base += 32) {
-        int cid = 0x7fffffff;
-        float s = -INFINITY;
+        // candidates whose approximate cosine cannot reach the current k-th best any more are dropped before the
+        // (expensive) exact scoring: |approx - exact| <= MARGIN, and the k-th best only rises
+        int cid0 = 0x7fffffff;
+        bool alive = false;
         if (base + lane < n) {
-            cid = cand[(size_t)q * CAP + base + lane];
-            const float* drow = docs + (size_t)(cid - id_base) * d;
+            const int2 c2 = cand[(size_t)q * CAP + base + lane];
+            cid0 = c2.x;
+            const float approx = __int_as_float(c2.y);
+            alive = (cnt < k) || !(approx + MARGIN < ls[k - 1]);  // NaN approx (zero-norm doc) stays alive
+        }
+        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+        const int na = __popc(alive_mask);
+        if (na == 0) continue;
+        // compact: lane c takes the c-th alive candidate
+        const int src_lane = lane < na ? __fns(alive_mask, 0, lane + 1) : 0;
+        int cid = __shfl_sync(0xffffffffu, cid0, src_lane);
+        if (lane >= na) cid = 0x7fffffff;
+        for (int c = 0; c < na; ++c) {
+            const int id = __shfl_sync(0xffffffffu, cid, c);
+            const float* drow = docs + (size_t)(id - id_base) * d;
+            for (int t = lane; t < d; t += 32) srow[c * (d + 1) + t] = __ldg(drow + t);
+        }
+        __syncwarp();
+        float s = -INFINITY;
+        if (lane < na) {
+            const float* mine = srow + lane * (d + 1);
             float acc = 0.f;
-            for (int t = 0; t < d; ++t) acc = __fadd_rn(acc, __fmul_rn(__ldg(qrow + t), __ldg(drow + t)));
+            for (int t = 0; t < d; ++t) acc = __fadd_rn(acc, __fmul_rn(sq[t], mine[t]));
             s = __fdiv_rn(acc, __fmul_rn(nqv, dn[cid - id_base]));
             if (s != s) s = -INFINITY;
             s = s + 0.0f;
         }
-        unsigned mask = __ballot_sync(0xffffffffu, base + lane < n);
+        __syncwarp();
+        unsigned mask = __ballot_sync(0xffffffffu, lane < na);
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -238,7 +311,8 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
 
 struct Ws {
     float *qn, *dn, *S, *run_s, *tq;
-    int *run_i, *run_cnt, *cand, *cand_cnt, *overflow;
+    int *run_i, *run_cnt, *cand_cnt, *overflow;
+    int2* cand;
     size_t bytes;
 };
 static Ws carve(void* ws, int nq, int64_t nd, int k) {
@@ -253,7 +327,7 @@ static Ws carve(void* ws, int nq, int64_t nd, int k) {
     w.run_i = a.take<int>((size_t)nq * k);
     w.run_cnt = a.take<int>(nq_pad);
     w.tq = a.take<float>(nq_pad);
-    w.cand = a.take<int>((size_t)nq_pad * CAP);
+    w.cand = a.take<int2>((size_t)nq_pad * CAP);
     w.cand_cnt = a.take<int>(nq_pad);
     w.overflow = a.take<int>(4);
     w.bytes = a.off;
@@ -292,7 +366,7 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     tkc::Ws w = tkc::carve(workspace, nq, nd, k);
     const int nq_pad = (nq + tkc::QT - 1) / tkc::QT * tkc::QT;
     static bool attr_set = false;
-    const size_t smem = 3 * (size_t)tkc::TILE_BYTES + 1024;
+    const size_t smem = 3 * (size_t)tkc::TILE_BYTES + (size_t)tkc::THREADS * 32 * sizeof(float) + 1024;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(tkc::topk_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -308,7 +382,13 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     const int seed = nd < tkc::SEED_DOCS ? (int)nd : tkc::SEED_DOCS;
     rc = topk_exact_chunk(Q, nq, docs, 0, seed, d, w.qn, w.dn, w.S, seed, id_offset, k, w.run_s, w.run_i, w.run_cnt, st);
     if (rc != DSSM_OK) return rc;
-    const size_t sel_smem = (size_t)4 * 2 * k * sizeof(float);
+    const size_t seed_smem = (size_t)4 * 2 * k * sizeof(float);
+    const size_t sel_smem = seed_smem + (size_t)4 * 33 * (d + 1) * sizeof(float);  // lists + per-warp row staging
+    static bool attr2_set = false;
+    if (!attr2_set) {
+        CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2_set = true;
+    }
     // thresholds from the seed (no candidates yet)
     tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt,
                                                                        w.run_s, w.run_i, w.run_cnt, w.tq);
@@ -323,7 +403,7 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
         if (splits > tiles) splits = tiles;
         const int tps = (tiles + splits - 1) / splits;
         dim3 grid(n_qtiles, (tiles + tps - 1) / tps);
-        tkc::topk_tc_filter_kernel<<<grid, tkc::THREADS, smem, st>>>(Q, nq, docs, lo, hi, w.dn, w.tq, id_offset, w.cand, w.cand_cnt,
+        tkc::topk_tc_filter_kernel<<<grid, tkc::THREADS, smem, st>>>(Q, nq, docs, lo, hi, w.dn, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
                                                                      w.overflow, tps);
         LAUNCH_CHECK("topk_tc_filter");
         tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand,
