@@ -19,6 +19,19 @@ def _free_port():
     return p
 
 
+def _join_all(ctx, seconds, what):
+    """mp.spawn(join=False).join() returns as soon as ONE process is done: loop until all are, with a deadline."""
+    import time
+
+    deadline = time.time() + seconds
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"{what} did not finish in {seconds} s")
+
+
 def _worker(rank, world, port, out, use_graph):
     import torch.distributed as dist
 
@@ -67,11 +80,7 @@ def test_two_gpu_data_parallel_matches_dp_oracle(tmp_path, use_graph):
 
     out = str(tmp_path / "rank0.npz")
     ctx = mp.spawn(_worker, args=(2, _free_port(), out, use_graph), nprocs=2, join=False)
-    ctx.join(timeout=240)
-    for p in ctx.processes:
-        if p.is_alive():
-            p.kill()
-            pytest.fail("data-parallel workers did not finish")
+    _join_all(ctx, 240, "data-parallel workers")
     got = np.load(out)
     conf = Config(TRIGRAM_D=21128, query_BS=100, NEG=4, layers=(300, 300, 128))
     params = init_params(conf, 0)
@@ -123,11 +132,7 @@ def test_two_gpu_sharded_retrieval_is_bit_exact(tmp_path):
 
     out = str(tmp_path / "r.npz")
     ctx = mp.spawn(_retrieval_worker, args=(2, _free_port(), out), nprocs=2, join=False)
-    ctx.join(timeout=240)
-    for p in ctx.processes:
-        if p.is_alive():
-            p.kill()
-            pytest.fail("retrieval workers did not finish")
+    _join_all(ctx, 240, "retrieval workers")
     got = np.load(out)
     rng = np.random.default_rng(0)
     Q = np.maximum(rng.standard_normal((96, 128)), 0).astype(np.float32)
