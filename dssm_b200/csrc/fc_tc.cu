@@ -328,6 +328,182 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant for the K-major contractions whose B operand is a pre-built weight image (forward, dX):
+//   warps 0-3  producers: stage the activation tile (register prefetch one k-block ahead, BN scale/shift from shared
+//              memory, hi/lo split, swizzled store), fence.proxy.async, arrive on full_a[stage]          (128 arrivals)
+//   warp 4     lane 0 issues the MMAs as soon as full_a / full_b of a stage have completed, tcgen05.commit -> empty
+//   warp 5     lane 0 streams the B image tiles with cp.async.bulk -> full_b (complete_tx), waiting on empty for reuse
+//   all 8 warps drain TMEM at the end.
+// No CTA-wide barrier inside the main loop: producers run up to STAGES k-blocks ahead of the tensor core.
+constexpr int WS_MAX_K = 512;  // scale/shift of both BN instances live in shared memory (8 KB static next to 217 KB dynamic)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
+    extern __shared__ char smem_raw[];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t full_a[STAGES];
+    __shared__ uint64_t full_b[STAGES];
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_scale[2][WS_MAX_K];
+    __shared__ __align__(16) float s_shift[2][WS_MAX_K];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
+    const int BN = g.BN;
+    const int b_tile_bytes = BN * BK * 4;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nkb = (g.K + BK - 1) / BK;
+    const int kpad = nkb * BK;
+
+    if (warp == 0) tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_a[s], 128);
+            mbar_init(&full_b[s], 1);
+        }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * kpad; i += THREADS) {  // identity prologue when there is no BN
+        const int seg = i / kpad, k = i - seg * kpad;
+        s_scale[seg][k] = (g.scale && k < g.K) ? __ldg(g.scale + seg * g.K + k) : 1.f;
+        s_shift[seg][k] = (g.scale && k < g.K) ? __ldg(g.shift + seg * g.K + k) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    const char* b_img = g.Bimg + (size_t)blockIdx.x * nkb * 2 * b_tile_bytes;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers (128 threads)
+        float4 cur[8], nxt[8];
+        auto load8 = [&](int kb, float4 (&q)[8]) {
+            const int k0 = kb * BK;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int id = tid + i * 128, r = id >> 3, c = id & 7;
+                const int m = m0 + r, k = k0 + c * 4;
+                q[i] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const float4*>(g.A + (size_t)m * g.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        load8(0, cur);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % STAGES, use = kb / STAGES;
+            if (kb + 1 < nkb) load8(kb + 1, nxt);
+            if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+            char* a_hi = smem + st * stage_bytes;
+            char* a_lo = a_hi + A_TILE_BYTES;
+            const int k0 = kb * BK;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int id = tid + i * 128, r = id >> 3, c = id & 7;
+                const int m = m0 + r, k = k0 + c * 4;
+                float4 v = cur[i];
+                if (m < g.M && k < g.K) {  // padding stays exactly zero
+                    const int seg = m < g.Bseg ? 0 : 1;
+                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg][k]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg][k]);
+                    v.x = act_fwd(fmaf(v.x, sc.x, sh.x), g.act);
+                    v.y = act_fwd(fmaf(v.y, sc.y, sh.y), g.act);
+                    v.z = act_fwd(fmaf(v.z, sc.z, sh.z), g.act);
+                    v.w = act_fwd(fmaf(v.w, sc.w, sh.w), g.act);
+                }
+                stage_chunk(a_hi, a_lo, r, c, v);
+            }
+            fence_proxy_async();  // this thread's generic-proxy writes -> visible to the tensor core
+            mbar_arrive(&full_a[st]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            const int nacc_used = nkb <= 12 ? 1 : NACC;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES, use = kb / STAGES;
+                mbar_wait(&full_a[st], (uint32_t)(use & 1));
+                mbar_wait(&full_b[st], (uint32_t)(use & 1));
+                tc_fence_after();
+                char* a_hi = smem + st * stage_bytes;
+                const uint64_t da_hi = make_desc_k_sw128(smem_u32(a_hi)), da_lo = make_desc_k_sw128(smem_u32(a_hi + A_TILE_BYTES));
+                const uint64_t db_hi = make_desc_k_sw128(smem_u32(a_hi + 2 * A_TILE_BYTES));
+                const uint64_t db_lo = make_desc_k_sw128(smem_u32(a_hi + 2 * A_TILE_BYTES + b_tile_bytes));
+                const uint32_t acc = tmem_d + (uint32_t)((kb % nacc_used) * MAX_BN);
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
+                    mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= nacc_used || ks > 0) ? 1u : 0u);
+                    mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                    mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
+                mma_commit(&empty_bar[st]);
+                if (kb == nkb - 1) mma_commit(&done_bar);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ B image loader
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES, use = kb / STAGES;
+                if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+                bulk_copy_g2s(smem + st * stage_bytes + 2 * A_TILE_BYTES, b_img + (size_t)kb * 2 * b_tile_bytes,
+                              (uint32_t)(2 * b_tile_bytes), &full_b[st]);
+            }
+        }
+    }
+    __syncwarp();
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+
+    // ---- epilogue (all 8 warps): TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
+    const int lane_grp = warp & 3;
+    const int row = m0 + lane_grp * 32 + lane;
+    const int nchunks = BN / 32;
+    const int nacc_e = nkb <= 12 ? 1 : (nkb < NACC ? nkb : NACC);
+    for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
+        for (int a = 1; a < nacc_e; ++a) {
+            uint32_t t[32];
+            tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+        }
+        if (row < g.M) {
+            const int nb = n0 + ch * 32;
+            float* out = g.D + (size_t)row * g.N + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (nb + j + 3 < g.N) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (g.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    *reinterpret_cast<float4*>(out + j) = o;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
 // Pre-split, pre-swizzled image of the weight operand B[n][k] for the K-major kernel, built once per call
 // (<= 820 KB): [n_tile][k_block][hi | lo][BN rows x 128 B].  transposed: B[n][k] = src[k*ld + n], else src[n*ld + k].
 __global__ void __launch_bounds__(256)
@@ -363,11 +539,15 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         attr_set = true;
     }
     if (splits > 0) {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM), splits);
         gemm_tc3_kernel<true><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
+    } else if (a.Bimg && a.K <= WS_MAX_K - BK) {
+        dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
+        gemm_tc3_ws_kernel<<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
     } else {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
         gemm_tc3_kernel<false><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);

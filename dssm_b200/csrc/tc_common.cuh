@@ -70,10 +70,12 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// round-to-nearest (ties away from zero) to tf32 = cvt.rna.tf32.f32, done with two full-rate integer instructions
+// instead of the quarter-rate conversion pipe: on a sign-magnitude format, adding half an ulp of the kept 10-bit
+// mantissa to the bit pattern and clearing the 13 dropped bits rounds the magnitude (carry into the exponent is the
+// correct round-up to the next binade).  The split kernels execute 16 of these per staged 16-byte chunk.
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 
