@@ -342,7 +342,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
+constexpr int WS_PRODUCERS = 256;             // warps 0-7
+constexpr int WS_THREADS = WS_PRODUCERS + 64;  // + warp 8 (MMA issuer) + warp 9 (B image loader)
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+    if (ACT == DSSM_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == DSSM_ACT_TANH) return tanhf(x);
+    return x;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
     extern __shared__ char smem_raw[];
     __shared__ uint64_t empty_bar[STAGES];
     __shared__ uint64_t full_a[STAGES];
@@ -365,13 +376,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&full_a[s], 128);
+            mbar_init(&full_a[s], WS_PRODUCERS);
             mbar_init(&full_b[s], 1);
         }
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * kpad; i += THREADS) {  // identity prologue when there is no BN
+    for (int i = tid; i < 2 * kpad; i += WS_THREADS) {  // identity prologue when there is no BN
         const int seg = i / kpad, k = i - seg * kpad;
         s_scale[seg][k] = (g.scale && k < g.K) ? __ldg(g.scale + seg * g.K + k) : 1.f;
         s_shift[seg][k] = (g.scale && k < g.K) ? __ldg(g.shift + seg * g.K + k) : 0.f;
@@ -382,48 +393,62 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
     const uint32_t tmem_d = tmem_base_slot;
     const char* b_img = g.Bimg + (size_t)blockIdx.x * nkb * 2 * b_tile_bytes;
 
-    if (warp < 4) {
-        // ------------------------------------------------------------------ producers (128 threads)
-        float4 cur[8], nxt[8];
-        auto load8 = [&](int kb, float4 (&q)[8]) {
-            const int k0 = kb * BK;
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers (256 threads, 4 chunks each)
+        // chunk i of this thread: tile row r_i = (tid + 256 i) / 8, 16-byte chunk c = tid % 8 -- all loop-invariant
+        const int c = tid & 7;
+        const float* rowp[4];
+        uint32_t off[4];
+        bool okm[4];
+        int seg[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int id = tid + i * 128, r = id >> 3, c = id & 7;
-                const int m = m0 + r, k = k0 + c * 4;
-                q[i] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const float4*>(g.A + (size_t)m * g.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const int r = (tid >> 3) + 32 * i;
+            const int m = m0 + r;
+            okm[i] = m < g.M;
+            seg[i] = m < g.Bseg ? 0 : 1;
+            rowp[i] = g.A + (size_t)(okm[i] ? m : 0) * g.K + c * 4;
+            off[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+        }
+        float4 cur[4], nxt[4];
+        auto load4 = [&](int kb, float4 (&q)[4]) {
+            const bool okk = kb * BK + c * 4 < g.K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                q[i] = (okm[i] && okk) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        load8(0, cur);
+        load4(0, cur);
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % STAGES, use = kb / STAGES;
-            if (kb + 1 < nkb) load8(kb + 1, nxt);
+            if (kb + 1 < nkb) load4(kb + 1, nxt);
             if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
             char* a_hi = smem + st * stage_bytes;
             char* a_lo = a_hi + A_TILE_BYTES;
-            const int k0 = kb * BK;
+            const int k = kb * BK + c * 4;
+            const bool okk = k < g.K;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int id = tid + i * 128, r = id >> 3, c = id & 7;
-                const int m = m0 + r, k = k0 + c * 4;
+            for (int i = 0; i < 4; ++i) {
                 float4 v = cur[i];
-                if (m < g.M && k < g.K) {  // padding stays exactly zero
-                    const int seg = m < g.Bseg ? 0 : 1;
-                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg][k]);
-                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg][k]);
-                    v.x = act_fwd(fmaf(v.x, sc.x, sh.x), g.act);
-                    v.y = act_fwd(fmaf(v.y, sc.y, sh.y), g.act);
-                    v.z = act_fwd(fmaf(v.z, sc.z, sh.z), g.act);
-                    v.w = act_fwd(fmaf(v.w, sc.w, sh.w), g.act);
+                if (okm[i] && okk) {  // padding stays exactly zero
+                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg[i]][k]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg[i]][k]);
+                    v.x = act_t<ACT>(fmaf(v.x, sc.x, sh.x));
+                    v.y = act_t<ACT>(fmaf(v.y, sc.y, sh.y));
+                    v.z = act_t<ACT>(fmaf(v.z, sc.z, sh.z));
+                    v.w = act_t<ACT>(fmaf(v.w, sc.w, sh.w));
                 }
-                stage_chunk(a_hi, a_lo, r, c, v);
+                float4 hi, lo;
+                hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+                lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+                *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
+                *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
             }
             fence_proxy_async();  // this thread's generic-proxy writes -> visible to the tensor core
             mbar_arrive(&full_a[st]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, BN);
@@ -449,8 +474,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
                 if (kb == nkb - 1) mma_commit(&done_bar);
             }
         }
-    } else if (warp == 5) {
-        // ------------------------------------------------------------------ B image loader
+    } else {
+        // ------------------------------------------------------------------ B image loader (warp 9)
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % STAGES, use = kb / STAGES;
@@ -461,45 +486,46 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_ws_kernel(Args g) {
         }
     }
     __syncwarp();
-    mbar_wait(&done_bar, 0);
-    tc_fence_after();
-
-    // ---- epilogue (all 8 warps): TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
-    const int lane_grp = warp & 3;
-    const int row = m0 + lane_grp * 32 + lane;
-    const int nchunks = BN / 32;
-    const int nacc_e = nkb <= 12 ? 1 : (nkb < NACC ? nkb : NACC);
-    for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
-        for (int a = 1; a < nacc_e; ++a) {
-            uint32_t t[32];
-            tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
+    if (warp < 8) {
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        // ---- epilogue (warps 0-7): TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
+        const int lane_grp = warp & 3;
+        const int row = m0 + lane_grp * 32 + lane;
+        const int nchunks = BN / 32;
+        const int nacc_e = nkb <= 12 ? 1 : (nkb < NACC ? nkb : NACC);
+        for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
+            for (int a = 1; a < nacc_e; ++a) {
+                uint32_t t[32];
+                tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
-        }
-        if (row < g.M) {
-            const int nb = n0 + ch * 32;
-            float* out = g.D + (size_t)row * g.N + nb;
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+            }
+            if (row < g.M) {
+                const int nb = n0 + ch * 32;
+                float* out = g.D + (size_t)row * g.N + nb;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (nb + j + 3 < g.N) {
-                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
-                    if (g.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int j = 0; j < 32; j += 4) {
+                    if (nb + j + 3 < g.N) {
+                        float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (g.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(out + j) = o;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
                     }
-                    *reinterpret_cast<float4*>(out + j) = o;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
                 }
             }
         }
+        tc_fence_before();
     }
-    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
@@ -539,7 +565,9 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         attr_set = true;
     }
     if (splits > 0) {
@@ -547,7 +575,9 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
         gemm_tc3_kernel<true><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
     } else if (a.Bimg && a.K <= WS_MAX_K - BK) {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
-        gemm_tc3_ws_kernel<<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
+        if (a.act == DSSM_ACT_RELU) gemm_tc3_ws_kernel<DSSM_ACT_RELU><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
+        else if (a.act == DSSM_ACT_TANH) gemm_tc3_ws_kernel<DSSM_ACT_TANH><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
+        else gemm_tc3_ws_kernel<DSSM_ACT_NONE><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
     } else {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
         gemm_tc3_kernel<false><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
