@@ -69,7 +69,8 @@ SIGNATURES = {
     "dssm_spmm_bwd_dw_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64]),
     "dssm_spmm_bwd_dw": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
     "dssm_spmm_bwd_csc_build": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),
-    "dssm_spmm_bwd_dw_range": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _sz, _p]),
+    "dssm_spmm_bwd_dw_range": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, _sz, _p]),
+    "dssm_spmm_bwd_dw_adam": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _p, _sz, _p]),
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),

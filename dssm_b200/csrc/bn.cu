@@ -295,6 +295,48 @@ bn_bwd_apply_kernel(float* __restrict__ dA, const float* __restrict__ H, int R, 
     }
 }
 
+// float4 variant (L % 4 == 0): one thread per 4 consecutive columns, EW4_ROWS rows in flight
+constexpr int EW4_ROWS = 8;
+__global__ void __launch_bounds__(128)
+bn_bwd_apply_v4_kernel(float4* __restrict__ dA, const float4* __restrict__ H, int R, int L4, int B, int act,
+                       const float4* __restrict__ gamma, const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                       const float4* __restrict__ scale, const float4* __restrict__ shift, const float4* __restrict__ dgamma,
+                       const float4* __restrict__ dbeta) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= L4) return;
+    const int r0 = blockIdx.x * EW4_ROWS;
+    float4 h[EW4_ROWS], d[EW4_ROWS];
+#pragma unroll
+    for (int j = 0; j < EW4_ROWS; ++j) {
+        const int r = r0 + j;
+        if (r < R) {
+            h[j] = __ldg(H + (size_t)r * L4 + c);
+            d[j] = dA[(size_t)r * L4 + c];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EW4_ROWS; ++j) {
+        const int r = r0 + j;
+        if (r >= R) continue;
+        const int seg = r < B ? 0 : 1;
+        const int o = seg * L4 + c;
+        const float inv_n = 1.0f / (seg == 0 ? (float)B : (float)(R - B));
+        const float4 sc = __ldg(scale + o), sh = __ldg(shift + o), rs = __ldg(rstd + o), mu = __ldg(mean + o), ga = __ldg(gamma + o),
+                     dg = __ldg(dgamma + o), db = __ldg(dbeta + o);
+        float4 out;
+#define BN_BWD1(x)                                                                  \
+    {                                                                               \
+        const float a = act_fwd(fmaf(h[j].x, sc.x, sh.x), act);                     \
+        const float g = d[j].x * act_grad_from_out(a, act);                         \
+        const float xhat = (h[j].x - mu.x) * rs.x;                                  \
+        out.x = (ga.x * rs.x) * (g - db.x * inv_n - xhat * (dg.x * inv_n));        \
+    }
+        BN_BWD1(x) BN_BWD1(y) BN_BWD1(z) BN_BWD1(w)
+#undef BN_BWD1
+        dA[(size_t)r * L4 + c] = out;
+    }
+}
+
 // no-BN mode: dH = dA * act'(act(H))
 __global__ void act_bwd_kernel(float* __restrict__ dA, const float* __restrict__ H, size_t total, int act) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -390,8 +432,15 @@ extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_
         db_combine_kernel<<<cdiv(L, 128), 128, 0, st>>>(db_seg, L, db);
         LAUNCH_CHECK("db_combine");
     }
-    bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift,
-                                                                 dgamma, dbeta);
+    if (L % 4 == 0 && aligned16(dA) && aligned16(H) && aligned16(gamma) && aligned16(mean) && aligned16(rstd) && aligned16(scale) &&
+        aligned16(shift) && aligned16(dgamma) && aligned16(dbeta)) {
+        dim3 grid(cdiv(R, EW4_ROWS), cdiv(L / 4, 128));
+        bn_bwd_apply_v4_kernel<<<grid, 128, 0, st>>>((float4*)dA, (const float4*)H, R, L / 4, B, act, (const float4*)gamma,
+                                                    (const float4*)mean, (const float4*)rstd, (const float4*)scale,
+                                                    (const float4*)shift, (const float4*)dgamma, (const float4*)dbeta);
+    } else {
+        bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift, dgamma, dbeta);
+    }
     LAUNCH_CHECK("bn_bwd_apply");
     return DSSM_OK;
 }

@@ -348,14 +348,54 @@ csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
     }
 }
 
+// Optional fusion of TF-Adam on W1 into the gather (single-GPU train step): the finished gradient row never goes to
+// HBM -- the warp that holds it updates w, m, v of that row in place.  Same arithmetic as adam_kernel (adam.cu).
+struct AdamW1 {
+    float4 *w, *m, *v;      // W1 and its Adam slots, [D, L1]
+    const float* beta_pow;  // device: beta1^t, beta2^t
+    float lr, b1, b2, eps;
+    const int* colcnt;      // columns without entries get the g = 0 update (dense-Adam semantics of the reference)
+};
+
 template <int NCH>
+__device__ __forceinline__ void adam_row(const AdamW1& a, int c, int L4, int lane, const float4 (&g)[NCH], float lr_t) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int col = lane + 32 * k;
+        if (col < L4) {
+            const size_t i = (size_t)c * L4 + col;
+            float4 pp = a.w[i], mm = a.m[i], vv = a.v[i];
+#define ADAM1(x)                                               \
+    {                                                          \
+        const float gr = g[k].x;                               \
+        mm.x = a.b1 * mm.x + (1.f - a.b1) * gr;                \
+        vv.x = a.b2 * vv.x + (1.f - a.b2) * (gr * gr);         \
+        pp.x = pp.x - lr_t * mm.x / (sqrtf(vv.x) + a.eps);     \
+    }
+            ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+            a.w[i] = pp;
+            a.m[i] = mm;
+            a.v[i] = vv;
+        }
+    }
+}
+
+// ASYNC: rows travel through the cp.async ring (best when dH is L2-resident and latency-bound, e.g. R = 6144);
+// otherwise through registers with GATHER_UNROLL loads in flight (measured faster when dH streams from HBM, R = 49152)
+template <int NCH, bool ASYNC, bool FUSE_ADAM>
 __global__ void __launch_bounds__(SPMM_THREADS)
 dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ itemptr, const int4* __restrict__ item_rec,
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
                     float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4,
-                    int col_begin, int col_end) {
+                    int col_begin, int col_end, AdamW1 adam) {
     extern __shared__ float4 ring_smem[];
+    float lr_t = 0.f;
+    if (FUSE_ADAM) {
+        const float b1p = __ldg(adam.beta_pow), b2p = __ldg(adam.beta_pow + 1);
+        lr_t = adam.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    }
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int stride = gridDim.x * wpb;
@@ -375,12 +415,19 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
         float4 acc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < e) gather_accumulate_async<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, ring, acc);
+        if (s < e) {
+            if (ASYNC) gather_accumulate_async<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, ring, acc);
+            else gather_accumulate<NCH>(csc_row, csc_val, s, e, dH4, L4, lane, acc);
+        }
         if (n_col_items == 1) {
+            if (FUSE_ADAM) {
+                adam_row<NCH>(adam, c, L4, lane, acc, lr_t);
+            } else {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int col = lane + 32 * k;
-                if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+                for (int k = 0; k < NCH; ++k) {
+                    const int col = lane + 32 * k;
+                    if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+                }
             }
         } else {
 #pragma unroll
@@ -409,14 +456,27 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                         }
                     }
                 }
+                if (FUSE_ADAM) {
+                    adam_row<NCH>(adam, c, L4, lane, acc, lr_t);
+                } else {
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    const int col = lane + 32 * k;
-                    if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+                    for (int k = 0; k < NCH; ++k) {
+                        const int col = lane + 32 * k;
+                        if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
+                    }
                 }
                 if (lane == 0) done[c] = 0;  // leave the counters clean for the next step
             }
         }
+    }
+    if (FUSE_ADAM) {
+        // columns absent from the batch: zero gradient, but m, v decay and w keeps moving on its momentum
+        float4 zero[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) zero[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int wpb2 = blockDim.x >> 5;
+        for (int c = col_begin + blockIdx.x * wpb2 + (threadIdx.x >> 5); c < col_end; c += gridDim.x * wpb2)
+            if (__ldg(adam.colcnt + c) == 0) adam_row<NCH>(adam, c, L4, lane, zero, lr_t);
     }
 }
 
@@ -450,19 +510,33 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
 
 template <int NCH>
 static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, int col_begin, int col_end,
-                             int chunk, cudaStream_t st) {
+                             int chunk, bool async, const AdamW1* adam, cudaStream_t st) {
     int blocks = sm_count() * 8;
     const int cols = col_end - col_begin;
     if (blocks > cols) blocks = cols > 0 ? cols : 1;
     const size_t smem = (size_t)(SPMM_THREADS / 32) * RING * NCH * 32 * sizeof(float4);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(dw_gather_v4_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(dw_gather_v4_kernel<NCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    dw_gather_v4_kernel<NCH><<<blocks, SPMM_THREADS, smem, st>>>(w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val,
-                                                            (const float4*)dH, (float4*)dW, (float4*)w.partial,
-                                                            w.done, w.next_item + chunk, D, L1 / 4, col_begin, col_end);
+    AdamW1 ad{};
+    if (adam) {
+        ad = *adam;
+        ad.colcnt = w.colcnt;
+        static bool attr2_set = false;
+        if (!attr2_set && smem > 48 * 1024) {
+            cudaFuncSetAttribute(dw_gather_v4_kernel<NCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr2_set = true;
+        }
+    }
+#define DW_ARGS w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val, (const float4*)dH, (float4*)dW, (float4*)w.partial, w.done, \
+                w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad
+    if (async && adam) dw_gather_v4_kernel<NCH, true, true><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
+    else if (async) dw_gather_v4_kernel<NCH, true, false><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
+    else if (adam) dw_gather_v4_kernel<NCH, false, true><<<blocks, SPMM_THREADS, 0, st>>>(DW_ARGS);
+    else dw_gather_v4_kernel<NCH, false, false><<<blocks, SPMM_THREADS, 0, st>>>(DW_ARGS);
+#undef DW_ARGS
 }
 
 template <int NCH>
@@ -573,7 +647,7 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
 
 // dW1 rows [col_begin, col_end) from the CSC in the workspace (every row of the range is written).  `chunk` selects
 // the work counter; use a different chunk id (< 64) for every range issued after one csc_build.
-extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
+extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t R, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
                                       int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(dH && dW1, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_range: null pointer");
     DSSM_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= D, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_range: bad column range");
@@ -584,8 +658,28 @@ extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, fl
     int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
     if (rc != DSSM_OK) return rc;
     const int nch = cdiv(L1 / 4, 32);
-    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, col_begin, col_end, chunk, (cudaStream_t)stream));
+    const bool async = (size_t)R * L1 * sizeof(float) <= ((size_t)32 << 20);  // dH comfortably L2-resident
+    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, col_begin, col_end, chunk, async, nullptr, (cudaStream_t)stream));
     LAUNCH_CHECK("dw_gather");
+    return DSSM_OK;
+}
+
+// Gather fused with TF-Adam on W1 (single-GPU train step): the gradient rows are consumed in registers, W1 / m / v are
+// updated in place (absent columns get the g = 0 update), dW1 is NOT produced.  beta_pow is read, not advanced.
+extern "C" int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, float* W1, float* m1, float* v1,
+                                     const float* beta_pow, float lr, float beta1, float beta2, float eps, void* workspace,
+                                     size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(dH && W1 && m1 && v1 && beta_pow, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_adam: null pointer");
+    DSSM_REQUIRE(L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_dw_adam: bad L1");
+    DSSM_REQUIRE(aligned16(dH) && aligned16(W1) && aligned16(m1) && aligned16(v1), DSSM_ERR_BAD_ALIGN, "dssm_spmm_bwd_dw_adam: buffers must be 16-byte aligned");
+    CscWorkspace w;
+    int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
+    if (rc != DSSM_OK) return rc;
+    AdamW1 ad{(float4*)W1, (float4*)m1, (float4*)v1, beta_pow, lr, beta1, beta2, eps, nullptr};
+    const int nch = cdiv(L1 / 4, 32);
+    const bool async = (size_t)R * L1 * sizeof(float) <= ((size_t)32 << 20);
+    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, nullptr, D, L1, 0, D, 0, async, &ad, (cudaStream_t)stream));
+    LAUNCH_CHECK("dw_gather_adam");
     return DSSM_OK;
 }
 
@@ -619,5 +713,5 @@ extern "C" int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, c
     int rc = dssm_spmm_bwd_csc_build(indptr, indices, values, R, D, L1, dW1, workspace, workspace_bytes, stream);
     if (rc != DSSM_OK) return rc;
     if (g_spmm_bwd_mid_event) CUDA_TRY(cudaEventRecord(g_spmm_bwd_mid_event, st));
-    return dssm_spmm_bwd_dw_range(dH, D, L1, dW1, 0, D, 0, workspace, workspace_bytes, stream);
+    return dssm_spmm_bwd_dw_range(dH, R, D, L1, dW1, 0, D, 0, workspace, workspace_bytes, stream);
 }

@@ -85,6 +85,7 @@ struct dssm_tower {
     cudaStream_t side;
     cudaEvent_t ev_fork, ev_join;
     bool csc_forked;
+    bool fuse_w1_adam;  // set for the duration of tower_step_impl: gather + Adam on W1 in one kernel, dW1 never stored
     cudaGraph_t graph_dp;  // forward + backward_begin (data-parallel pipeline)
     cudaGraphExec_t graph_dp_exec;
     int64_t launches_per_dp;
@@ -233,6 +234,7 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->csc_forked = false;
     t->img_forked = false;
     t->launches = 0;
+    t->fuse_w1_adam = false;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
     return DSSM_OK;
@@ -363,8 +365,9 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         t->img_forked = true;
     }
     if (fork_csc) {
-        TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1], t->grads_p ? t->G_("W1") : nullptr, t->sp_ws,
-                                    t->sp_ws_bytes, (dssm_stream_t)t->side));
+        TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1],
+                                    (t->grads_p && !t->fuse_w1_adam) ? t->G_("W1") : nullptr, t->sp_ws, t->sp_ws_bytes,
+                                    (dssm_stream_t)t->side));
         CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
         t->csc_forked = true;
     }
@@ -442,8 +445,14 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
                 CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join, 0));
                 t->csc_forked = false;
-                if (w1_mode == 0)
-                    TRY(dssm_spmm_bwd_dw_range(t->dh[1], t->D, t->L[1], t->G_("W1"), 0, t->D, 0, t->sp_ws, t->sp_ws_bytes, s));
+                if (w1_mode == 0 && t->fuse_w1_adam) {
+                    const int wi = t->find(t->params, "W1");
+                    const int64_t wo = t->params[wi].off;
+                    TRY(dssm_spmm_bwd_dw_adam(t->dh[1], R, t->D, t->L[1], t->params_p + wo, t->m_p + wo, t->v_p + wo, t->beta_pow_p,
+                                              c.learning_rate, c.beta1, c.beta2, c.adam_eps, t->sp_ws, t->sp_ws_bytes, s));
+                } else if (w1_mode == 0) {
+                    TRY(dssm_spmm_bwd_dw_range(t->dh[1], R, t->D, t->L[1], t->G_("W1"), 0, t->D, 0, t->sp_ws, t->sp_ws_bytes, s));
+                }
             } else if (w1_mode == 1) {
                 DSSM_REQUIRE(t->L[1] % 4 == 0 && t->L[1] <= 1024, DSSM_ERR_BAD_SHAPE, "chunked dW1 needs L1 %% 4 == 0");
                 TRY(dssm_spmm_bwd_csc_build(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->L[1], t->G_("W1"), t->sp_ws,
@@ -519,7 +528,7 @@ extern "C" int dssm_tower_backward_w1(dssm_tower* t, int32_t chunk, int32_t n_ch
     LaunchScope ls(t);
     int c0, c1;
     w1_chunk_cols(t, chunk, n_chunks, &c0, &c1);
-    return dssm_spmm_bwd_dw_range(t->dh[1], t->D, t->L[1], t->G_("W1"), c0, c1, chunk, t->sp_ws, t->sp_ws_bytes, stream);
+    return dssm_spmm_bwd_dw_range(t->dh[1], t->R, t->D, t->L[1], t->G_("W1"), c0, c1, chunk, t->sp_ws, t->sp_ws_bytes, stream);
 }
 
 extern "C" int dssm_tower_adam_range(dssm_tower* t, int64_t offset_floats, int64_t count_floats, float grad_scale,
@@ -549,10 +558,23 @@ extern "C" int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t st
 
 static int tower_step_impl(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
                            dssm_stream_t s) {
-    TRY(tower_forward_impl(t, indptr, indices, values, 1, 1, true, s));
-    TRY(tower_backward_impl(t, s));
+    const dssm_config& c = t->cfg;
+    // single-GPU step: W1's Adam update rides on the dW1 gather (the CSC is built beside the forward) unless the
+    // step is being phase-profiled or FC1's width rules out the vector kernels
+    const int wi = t->find(t->params, "W1");
+    const bool fuse = t->L[1] % 4 == 0 && t->L[1] <= 1024 && !(g_timer && g_timer->on) && t->params[wi].off == 0;
+    t->fuse_w1_adam = fuse;
+    int rc = tower_forward_impl(t, indptr, indices, values, 1, 1, true, s);
+    if (rc == DSSM_OK) rc = tower_backward_impl(t, s);
+    t->fuse_w1_adam = false;
     t->fwd_train_done = false;
-    TRY(tower_adam_impl(t, 1.0f, s));
+    if (rc != DSSM_OK) return rc;
+    if (!fuse) return tower_adam_impl(t, 1.0f, s);
+    // the rest of the flat buffer (everything behind W1), then the beta powers
+    const int64_t w1_end = pad4((int64_t)t->D * t->L[1]);
+    TRY(dssm_adam_step(t->params_p + w1_end, t->grads_p + w1_end, t->m_p + w1_end, t->v_p + w1_end, t->P - w1_end, t->beta_pow_p,
+                       c.learning_rate, c.beta1, c.beta2, c.adam_eps, 1.0f, s));
+    TRY(dssm_adam_advance(t->beta_pow_p, c.beta1, c.beta2, s));
     return DSSM_OK;
 }
 

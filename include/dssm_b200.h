@@ -110,8 +110,15 @@ int dssm_spmm_bwd_dw(const int32_t* indptr, const int32_t* indices, const float*
 int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* indices, const float* values, int32_t R, int32_t D,
                             int32_t L1, float* dW1 /* zero-filled here: rows of absent columns get no other write */,
                             void* workspace, size_t workspace_bytes, dssm_stream_t stream);
-int dssm_spmm_bwd_dw_range(const float* dH, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
+int dssm_spmm_bwd_dw_range(const float* dH, int32_t R, int32_t D, int32_t L1, float* dW1, int32_t col_begin, int32_t col_end,
                            int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+
+/* The gather fused with tf.train.AdamOptimizer on weight1 (new_dssm.py:217) for the single-GPU step: after
+ * dssm_spmm_bwd_csc_build(dW1 = NULL), every dW1 row is consumed in registers and W1 / m / v are updated in place
+ * (columns absent from the batch get the zero-gradient update: dense-Adam semantics); dW1 itself is not produced. */
+int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, float* W1, float* m1, float* v1,
+                          const float* beta_pow, float lr, float beta1, float beta2, float eps, void* workspace,
+                          size_t workspace_bytes, dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
