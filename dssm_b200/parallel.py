@@ -73,14 +73,15 @@ class DataParallelTower:
                 t.backward_w1(k, n)
             t.adam(grad_scale=1.0)
             return
-        # [grads beyond W1 | EMA shadows] are contiguous in tower.comm: one collective
-        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         works = []
         for k in range(n):
             t.backward_w1(k, n)
             off, cnt = t.w1_chunk(k, n)
             if cnt:
                 works.append((off, cnt, dist.all_reduce(t.grads[off:off + cnt], op=dist.ReduceOp.AVG, group=self.group, async_op=True)))
+        # [grads beyond W1 | EMA shadows] are contiguous in tower.comm: one small collective, queued BEHIND the W1
+        # chunks so that its latency does not delay the large transfers (it is only needed by the last Adam call)
+        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         for off, cnt, w in works:
             w.wait()
             t.adam_range(off, cnt, 1.0)

@@ -183,7 +183,8 @@ def test_host_step_graph_and_sess_run_shim():
         la = a.train_step(a.to_device(bt)).item()
         lb = b_.train_step_host(b_.pin(bt))
         lc = c.train_step_host(c.pin(bt))
-        assert abs(la - lb) <= 1e-5 * abs(la) and abs(la - lc) <= 1e-5 * abs(la)
+        # same kernels; only the atomic slot order inside dW1's columns differs run to run, which Adam amplifies
+        assert abs(la - lb) <= 2e-4 * abs(la) and abs(la - lc) <= 2e-4 * abs(la)
     pa, pb, pc = a.export_params(), b_.export_params(), c.export_params()
     # same kernels, same order: only the atomic slot order inside dW1's columns can differ between runs
     assert_update_close(pb, pa, params, conf.use_bn, "host path", l2_tol=2e-2)
@@ -293,3 +294,49 @@ def test_chunked_backward_equals_monolithic():
         # same gradients up to the atomic slot order inside dW1's columns; Adam amplifies that (helpers.assert_update_close)
         assert_update_close(t.export_params(), ref.export_params(), params, conf.use_bn, f"chunked adam (n={n})", l2_tol=1e-3)
         assert torch.equal(t.beta_pow, ref.beta_pow)
+
+
+def test_embed_docs_feeds_retrieval():
+    """Eval-mode embeddings of arbitrary rows (the corpus builder) equal the oracle's eval forward, and the corpus
+    matrix they produce goes through corpus_topk with the oracle's ids."""
+    from dssm_b200 import Config, DSSMTower, corpus_topk
+    from dssm_b200.export import embed_docs, embed_queries
+    from dssm_b200.synthetic import init_params, make_batch, sparse_rows
+    from oracle import DSSMOracle, corpus_topk_oracle
+
+    conf = Config(TRIGRAM_D=5000, query_BS=16, NEG=3, layers=(64, 128), gemm_mode="tc_3xtf32")
+    params = init_params(conf, 0)
+    b = [make_batch(conf, s, 6, 12) for s in range(2)]
+    t = DSSMTower(conf, max_nnz=4096, params=params)
+    orc = DSSMOracle(oracle_config(conf), params)
+    for x in b:  # populate the EMA shadows identically (forward only, no parameter update)
+        t.forward(t.to_device(x), on_train=True)
+        orc.forward(x.to_scipy(), on_train=True)
+    rng = np.random.Generator(np.random.PCG64(5))
+    docs = sparse_rows(rng, 150, conf.TRIGRAM_D, 12.0)  # 150 rows: not a multiple of the 64 doc slots per batch
+    queries = sparse_rows(rng, 21, conf.TRIGRAM_D, 6.0)
+    E = embed_docs(t, docs)
+    Qe = embed_queries(t, queries)
+    # oracle: eval forward of batches holding the same rows in the doc / query slots
+    import scipy.sparse as sp
+
+    def oracle_embed(rows, seg):
+        out = []
+        per = conf.query_BS if seg == "q" else 4 * conf.query_BS
+        for lo in range(0, rows.shape[0], per):
+            chunk = rows[lo:lo + per]
+            pad = per - chunk.shape[0]
+            if pad:
+                chunk = sp.vstack([chunk] + [rows[:1]] * pad, format="csr")
+            other = sp.vstack([rows[:1]] * (4 * conf.query_BS if seg == "q" else conf.query_BS), format="csr")
+            X = sp.vstack([chunk, other] if seg == "q" else [other, chunk], format="csr")
+            Y = orc.forward(X, on_train=False)["Y"]
+            part = Y[:conf.query_BS] if seg == "q" else Y[conf.query_BS:]
+            out.append(part[:per - pad])
+        return np.concatenate(out)
+
+    assert_close(E, oracle_embed(docs, "d"), FWD_TOL, "embed_docs")
+    assert_close(Qe, oracle_embed(queries, "q"), FWD_TOL, "embed_queries")
+    s, i = corpus_topk(torch.from_numpy(Qe).cuda(), torch.from_numpy(E).cuda(), 10)
+    rs, ri = corpus_topk_oracle(Qe, E, 10)
+    assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy(), rs)
