@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import (GOLDEN_CASES, assert_close, assert_grads_close, assert_update_close, grad_tolerances, load_golden,
+from tests.helpers import (GOLDEN_CASES, assert_close, assert_grads_close, assert_update_close, gpu_relu_masks,
+                           grad_tolerances, load_golden,
                            oracle_config, rel_err, tf_adam_reference, to_stacked)
 
 pytestmark = pytest.mark.gpu
@@ -340,3 +341,29 @@ def test_embed_docs_feeds_retrieval():
     s, i = corpus_topk(torch.from_numpy(Qe).cuda(), torch.from_numpy(E).cuda(), 10)
     rs, ri = corpus_topk_oracle(Qe, E, 10)
     assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy(), rs)
+
+
+@pytest.mark.parametrize("name", ["C2", "C4", "C4_NOBN"])
+def test_full_size_baseline_configs_against_oracle(name):
+    """BASELINE.json configs at their full sizes (C2: B=1024, NEG=4; C4: B=1024, NEG=50 with and without BN): one
+    training step against the oracle -- loss and cosines at 1e-5, every gradient at the bounds of grad_tolerances,
+    the oracle differentiating with the device's relu active set (helpers.align_relu_masks: the two sets may differ only
+    at units within helpers.KINK_TOL of the kink)."""
+    from dssm_b200 import DSSMTower, baseline_config
+    from dssm_b200.synthetic import init_params, make_batch
+
+    conf = baseline_config(name)
+    vm = "tfidf" if name == "C4_NOBN" else "count"  # dssm_no_bn/dssm_tf_idf.py:37 feeds real-valued features
+    b = make_batch(conf, seed=3, value_mode=vm)
+    params = init_params(conf, 0)
+    t = DSSMTower(conf, max_nnz=b.nnz, params=params)
+    X = b.to_scipy()
+    loss = t.forward(t.to_device(b), on_train=True)
+    g64, allow, c64 = grad_tolerances(conf, X, params, GRAD_TOL, masks=gpu_relu_masks(conf, t))
+    assert c64["kink_flips"] <= 1e-5 * sum(c64[f"a{l}"].size for l in range(1, len(conf.layers) + 1)) + 4
+    assert np.isfinite(float(c64["loss"]))
+    assert abs(loss.item() - float(c64["loss"])) <= FWD_TOL * abs(float(c64["loss"]))
+    assert_close(t.tensor("cos_sim_raw").cpu().numpy().ravel(), c64["cos_sim_raw"], FWD_TOL, "cos_sim_raw")
+    assert_close(t.tensor("Y").cpu().numpy(), c64["Y"], FWD_TOL, "Y")
+    t.backward()
+    assert_grads_close(conf, t.export_grads(), g64, allow, c64)
