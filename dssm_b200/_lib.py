@@ -70,7 +70,8 @@ SIGNATURES = {
     "dssm_spmm_bwd_dw": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
     "dssm_spmm_bwd_csc_build": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "dssm_spmm_bwd_dw_range": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, _sz, _p]),
-    "dssm_spmm_bwd_dw_adam": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _p, _sz, _p]),
+    "dssm_spmm_bwd_dw_adam": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _i32, _p, _sz, _p]),
+    "dssm_spmm_bwd_adam_absent": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _p, _sz, _p]),
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
@@ -118,6 +119,8 @@ SIGNATURES = {
     "dssm_tower_train_step_staged": (C.c_int, [_p, _p]),
     "dssm_tower_launch_count": (_i64, [_p]),
     "dssm_tower_profile_step": (C.c_int, [_p, C.POINTER(C.c_float), _p]),
+    "dssm_tower_profile_step_overlapped": (C.c_int, [_p, C.POINTER(C.c_float), _p]),
+    "dssm_tower_profile_timeline": (C.c_int, [_p, C.c_char_p, _i32, C.POINTER(C.c_float), _i32, C.POINTER(_i32), _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

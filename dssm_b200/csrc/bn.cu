@@ -11,7 +11,8 @@ namespace dssm {
 constexpr int BN_CHUNK_ROWS = 256;  // minimum rows per partial (workspace sizing uses this)
 constexpr int BN_MAX_CHUNKS = 32;   // per segment: keeps the serial merge in the finalize kernels short
 constexpr int BN_TX = 32;           // columns per block
-constexpr int BN_TY = 8;            // row lanes per block
+constexpr int BN_TY = 32;           // row lanes per block, forward: a 256-row chunk is ONE round of MLP loads per thread
+constexpr int BN_TY_BWD = 16;       // backward (two operands, ~64 registers): 512 threads so that two blocks share an SM
 constexpr int MLP = 8;              // independent row loads in flight per thread in the column reductions
 
 // chunk table: chunks never straddle the segment boundary
@@ -24,10 +25,61 @@ static inline int bn_chunk_rows(int R, int B) {
     return cr < BN_CHUNK_ROWS ? BN_CHUNK_ROWS : cr;
 }
 
+// "last block finalizes": every block of one 32-column strip takes a ticket after publishing its partials; the block
+// that draws the last ticket merges the strip (fixed ascending chunk order, so the result does not depend on which
+// block that is) and puts the ticket counter back to zero.  Saves a dependent launch per reduction.
+__device__ __forceinline__ bool last_block_of_strip(int* tickets, int n_blocks) {
+    __shared__ int s_last;
+    __threadfence();  // partials of this block visible device-wide before the ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int prev = atomicAdd(tickets + blockIdx.x, 1);
+        s_last = prev == n_blocks - 1;
+        if (s_last) tickets[blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+struct BnFinalize {  // outputs of the forward finalize, all [2][L]
+    const float *gamma, *beta;
+    float *ema_mean, *ema_var, *mean, *var, *rstd, *scale, *shift;
+    float eps, decay;
+    int update_ema, nq_chunks;
+};
+
+__device__ __forceinline__ void bn_write_affine(const BnFinalize& f, int i, float mean, float var) {
+    const float rstd = 1.0f / sqrtf(var + f.eps);
+    const float sc = rstd * f.gamma[i];
+    f.mean[i] = mean;
+    f.var[i] = var;
+    f.rstd[i] = rstd;
+    f.scale[i] = sc;
+    f.shift[i] = f.beta[i] - mean * sc;
+}
+
+// The strip's partials [planes][n_chunks][32 columns] staged in shared memory by the whole block (one L2 round trip
+// instead of one per chunk in a serial merge).
+template <int PLANES>
+__device__ __forceinline__ void load_strip_partials(const float* __restrict__ part, int n_chunks_total, int L, float* s_part) {
+    const int t = threadIdx.y * BN_TX + threadIdx.x;
+    const int total = PLANES * n_chunks_total * BN_TX;
+    const int col0 = blockIdx.x * BN_TX;
+    for (int e = t; e < total; e += BN_TX * (int)blockDim.y) {
+        const int pc = e / BN_TX, cx = e - pc * BN_TX;  // pc = plane * n_chunks_total + chunk
+        s_part[e] = col0 + cx < L ? __ldcg(part + (size_t)pc * L + col0 + cx) : 0.f;
+    }
+    __syncthreads();
+}
+
 // partial layout: [3][n_chunks_total][L]  (count as float, mean, M2)
 __global__ void __launch_bounds__(BN_TX * BN_TY)
-bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
+bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restrict__ part, int n_chunks_total, int chunk_rows,
+                int* __restrict__ tickets, BnFinalize fin) {
     __shared__ float red[BN_TY][BN_TX + 1];
+    __shared__ float red2[BN_TY][BN_TX + 1];
+    __shared__ float s_part[3 * 2 * BN_MAX_CHUNKS * BN_TX];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
     const int nq = bn_chunks_of(B, chunk_rows);
@@ -58,14 +110,18 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
                 q = fmaf(d, d, q);
             }
         }
-#pragma unroll 1
-        for (; r < r1; r += BN_TY) {
-            const float d = __ldg(X + (size_t)r * L + col) - K;
-            s += d;
-            q = fmaf(d, d, q);
+        {   // remainder (< MLP rows per thread), still issued together
+            float v[MLP];
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) v[u] = (r + u * BN_TY < r1) ? __ldg(X + (size_t)(r + u * BN_TY) * L + col) : K;
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                const float d = v[u] - K;  // exactly 0 for the padding
+                s += d;
+                q = fmaf(d, d, q);
+            }
         }
     }
-    __shared__ float red2[BN_TY][BN_TX + 1];
     red[ty][tx] = s;
     red2[ty][tx] = q;
     __syncthreads();
@@ -78,65 +134,41 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
         part[((size_t)1 * n_chunks_total + chunk) * L + col] = K + md;
         part[((size_t)2 * n_chunks_total + chunk) * L + col] = fmaxf(tq - ts * md, 0.f);
     }
+    if (!last_block_of_strip(tickets, n_chunks_total)) return;
+    load_strip_partials<3>(part, n_chunks_total, L, s_part);
+    // thread rows 0 / 1 merge the query / doc segment of their column: chunk triples (n, mean, M2) in ascending
+    // order with Chan's formula
+    if (ty >= 2 || col >= L) return;
+    const int seg = ty;
+    const int c0 = seg == 0 ? 0 : fin.nq_chunks;
+    const int c1 = seg == 0 ? fin.nq_chunks : n_chunks_total;
+    if (c0 == c1) return;  // empty segment (single-instance call, B == R)
+    float cn = 0.f, mu = 0.f, m2 = 0.f;
+    for (int c = c0; c < c1; ++c) {
+        const float nb = s_part[(0 * n_chunks_total + c) * BN_TX + tx];
+        const float mb = s_part[(1 * n_chunks_total + c) * BN_TX + tx];
+        const float qb = s_part[(2 * n_chunks_total + c) * BN_TX + tx];
+        const float nt = cn + nb;
+        const float delta = mb - mu;
+        mu = mu + delta * (nb / nt);
+        m2 = m2 + qb + delta * delta * (cn * nb / nt);
+        cn = nt;
+    }
+    const int i = seg * L + col;
+    const float var = m2 / cn;  // biased (tf.nn.moments)
+    if (fin.update_ema) {
+        // ExponentialMovingAverage.apply: shadow -= (1 - decay) * (shadow - value), new_dssm.py:78-81
+        const float em = fin.ema_mean[i], ev = fin.ema_var[i];
+        fin.ema_mean[i] = em - (1.f - fin.decay) * (em - mu);
+        fin.ema_var[i] = ev - (1.f - fin.decay) * (ev - var);
+    }
+    bn_write_affine(fin, i, mu, var);
 }
 
-// one warp per (segment, column): lane c holds chunk c's (n, mean, M2) -- at most BN_MAX_CHUNKS = 32 chunks per
-// segment by construction -- merged by a fixed shuffle tree with Chan's formula; lane 0 writes EMA, scale/shift
-__global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, int on_train, int update_ema,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ema_mean,
-                   float* __restrict__ ema_var, float eps, float decay, float* __restrict__ mean_o, float* __restrict__ var_o,
-                   float* __restrict__ rstd_o, float* __restrict__ scale_o, float* __restrict__ shift_o) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= 2 * L) return;
-    const int seg = i / L, col = i - seg * L;
-    float mean, var;
-    if (on_train) {
-        const int c0 = seg == 0 ? 0 : nq_chunks;
-        const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
-        if (c0 == c1) return;  // empty segment (single-instance call, B == R)
-        float n = 0.f, mu = 0.f, m2 = 0.f;
-        if (c0 + lane < c1) {
-            const int c = c0 + lane;
-            n = part[((size_t)0 * n_chunks_total + c) * L + col];
-            mu = part[((size_t)1 * n_chunks_total + c) * L + col];
-            m2 = part[((size_t)2 * n_chunks_total + c) * L + col];
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {  // lane l absorbs lane l+o: chunks stay merged in ascending order
-            const float nb = __shfl_down_sync(0xffffffffu, n, o);
-            const float mb = __shfl_down_sync(0xffffffffu, mu, o);
-            const float qb = __shfl_down_sync(0xffffffffu, m2, o);
-            const float nt = n + nb;
-            if (nb > 0.f && (lane & (2 * o - 1)) == 0) {
-                const float delta = mb - mu;
-                mu = mu + delta * (nb / nt);
-                m2 = m2 + qb + delta * delta * (n * nb / nt);
-                n = nt;
-            }
-        }
-        if (lane != 0) return;
-        mean = mu;
-        var = m2 / n;  // biased (tf.nn.moments)
-        if (update_ema) {
-            // ExponentialMovingAverage.apply: shadow -= (1 - decay) * (shadow - value), new_dssm.py:78-81
-            const float em = ema_mean[i], ev = ema_var[i];
-            ema_mean[i] = em - (1.f - decay) * (em - mean);
-            ema_var[i] = ev - (1.f - decay) * (ev - var);
-        }
-    } else {
-        if (lane != 0) return;
-        mean = ema_mean[i];
-        var = ema_var[i];
-    }
-    const float rstd = 1.0f / sqrtf(var + eps);
-    const float sc = rstd * gamma[i];
-    mean_o[i] = mean;
-    var_o[i] = var;
-    rstd_o[i] = rstd;
-    scale_o[i] = sc;
-    shift_o[i] = beta[i] - mean * sc;
+// inference (new_dssm.py:85-86): the moments are the EMA shadows
+__global__ void __launch_bounds__(256) bn_eval_affine_kernel(int L, BnFinalize fin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * L) bn_write_affine(fin, i, fin.ema_mean[i], fin.ema_var[i]);
 }
 
 constexpr int EW_ROWS = 4;  // rows per block iteration of the elementwise kernels
@@ -164,13 +196,16 @@ bn_act_apply_kernel(const float* __restrict__ X, int R, int L, int B, const floa
 
 // ---- backward -------------------------------------------------------------------------------------
 // pass 1: per chunk column sums of g = dA*act'(a) and g*xhat  -> part [2][n_chunks_total][L]
-__global__ void __launch_bounds__(BN_TX * BN_TY)
+__global__ void __launch_bounds__(BN_TX * BN_TY_BWD)
 bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, int R, int L, int B, int act,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
-                     const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total, int chunk_rows) {
-    __shared__ float red0[BN_TY][BN_TX + 1];
-    __shared__ float red1[BN_TY][BN_TX + 1];
-    __shared__ float red2[BN_TY][BN_TX + 1];
+                     const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total, int chunk_rows,
+                     int* __restrict__ tickets, const float* __restrict__ gamma, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ db /* [L] or NULL */) {
+    __shared__ float red0[BN_TY_BWD][BN_TX + 1];
+    __shared__ float red1[BN_TY_BWD][BN_TX + 1];
+    __shared__ float red2[BN_TY_BWD][BN_TX + 1];
+    __shared__ float s_part[3 * 2 * BN_MAX_CHUNKS * BN_TX];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int col = blockIdx.x * BN_TX + tx;
     const int nq = bn_chunks_of(B, chunk_rows);
@@ -185,12 +220,12 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
         const int o = seg * L + col;
         const float mu = __ldg(mean + o), rs = __ldg(rstd + o), sc = __ldg(scale + o), sh = __ldg(shift + o);
         int r = r0 + ty;
-        for (; r + (MLP - 1) * BN_TY < r1; r += MLP * BN_TY) {
+        for (; r + (MLP - 1) * BN_TY_BWD < r1; r += MLP * BN_TY_BWD) {
             float hv[MLP], dv[MLP];
 #pragma unroll
             for (int u = 0; u < MLP; ++u) {
-                hv[u] = __ldg(H + (size_t)(r + u * BN_TY) * L + col);
-                dv[u] = __ldg(dA + (size_t)(r + u * BN_TY) * L + col);
+                hv[u] = __ldg(H + (size_t)(r + u * BN_TY_BWD) * L + col);
+                dv[u] = __ldg(dA + (size_t)(r + u * BN_TY_BWD) * L + col);
             }
 #pragma unroll
             for (int u = 0; u < MLP; ++u) {
@@ -202,14 +237,25 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
                 sx += xh;
             }
         }
-        for (; r < r1; r += BN_TY) {
-            const float h = __ldg(H + (size_t)r * L + col);
-            const float a = act_fwd(fmaf(h, sc, sh), act);
-            const float g = __ldg(dA + (size_t)r * L + col) * act_grad_from_out(a, act);
-            const float xh = (h - mu) * rs;
-            sg += g;
-            sgx = fmaf(g, xh, sgx);
-            sx += xh;
+        {   // remainder (< MLP rows per thread), still issued together
+            float hv[MLP], dv[MLP];
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                const bool ok = r + u * BN_TY_BWD < r1;
+                hv[u] = ok ? __ldg(H + (size_t)(r + u * BN_TY_BWD) * L + col) : 0.f;
+                dv[u] = ok ? __ldg(dA + (size_t)(r + u * BN_TY_BWD) * L + col) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < MLP; ++u) {
+                if (r + u * BN_TY_BWD < r1) {
+                    const float a = act_fwd(fmaf(hv[u], sc, sh), act);
+                    const float g = dv[u] * act_grad_from_out(a, act);
+                    const float xh = (hv[u] - mu) * rs;
+                    sg += g;
+                    sgx = fmaf(g, xh, sgx);
+                    sx += xh;
+                }
+            }
         }
     }
     red0[ty][tx] = sg;
@@ -219,48 +265,41 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
     if (ty == 0 && col < L) {
         float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < BN_TY; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; t2 += red2[i][tx]; }
+        for (int i = 0; i < BN_TY_BWD; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; t2 += red2[i][tx]; }
         part[((size_t)0 * n_chunks_total + chunk) * L + col] = t0;
         part[((size_t)1 * n_chunks_total + chunk) * L + col] = t1;
         part[((size_t)2 * n_chunks_total + chunk) * L + col] = t2;
     }
-}
-
-// dgamma, dbeta per (segment, column); optionally the pre-BN bias gradient db[c] = sum_r dH[r,c].  Under BN that sum
-// is identically  -gamma*rstd*dgamma*(sum_r xhat)/n  per segment (the g and dbeta terms cancel exactly), i.e. rounding
-// noise around zero -- evaluated here from sum xhat accumulated in the same pass instead of another sweep over dH.
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ part, int n_chunks_total, int nq_chunks, int L, int B, int R,
-                       const float* __restrict__ gamma, const float* __restrict__ rstd, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ db_seg /* [2][L] or NULL */) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= 2 * L) return;
-    const int seg = i / L, col = i - seg * L;
-    const int c0 = seg == 0 ? 0 : nq_chunks;
-    const int c1 = seg == 0 ? nq_chunks : n_chunks_total;
-    float b = 0.f, g = 0.f, x = 0.f;
-    for (int c = c0 + lane; c < c1; c += 32) {
-        b += part[((size_t)0 * n_chunks_total + c) * L + col];
-        g += part[((size_t)1 * n_chunks_total + c) * L + col];
-        x += part[((size_t)2 * n_chunks_total + c) * L + col];
-    }
-    b = warp_sum(b);
-    g = warp_sum(g);
-    x = warp_sum(x);
-    if (lane == 0) {
-        dbeta[i] = b;
-        dgamma[i] = g;
-        if (db_seg) {
-            const float n = seg == 0 ? (float)B : (float)(R - B);
-            db_seg[i] = n > 0.f ? -(gamma[i] * rstd[i]) * g * (x / n) : 0.f;
+    if (!last_block_of_strip(tickets, n_chunks_total)) return;
+    // dgamma, dbeta per (segment, column); optionally the pre-BN bias gradient db[c] = sum_r dH[r,c].  Under BN that
+    // sum is identically  -gamma*rstd*dgamma*(sum_r xhat)/n  per segment (the g and dbeta terms cancel exactly), i.e.
+    // rounding noise around zero -- evaluated from sum xhat of the same pass instead of another sweep over dH.
+    load_strip_partials<3>(part, n_chunks_total, L, s_part);
+    float* s_db = &red0[0][0];  // [2][BN_TX + 1], free after the block reduction above
+    if (ty < 2) {
+        float dbv = 0.f;
+        if (col < L) {
+            const int sg_ = ty;
+            const int c0 = sg_ == 0 ? 0 : nq;
+            const int c1 = sg_ == 0 ? nq : n_chunks_total;
+            float b = 0.f, g = 0.f, x = 0.f;
+            for (int c = c0; c < c1; ++c) {
+                b += s_part[(0 * n_chunks_total + c) * BN_TX + tx];
+                g += s_part[(1 * n_chunks_total + c) * BN_TX + tx];
+                x += s_part[(2 * n_chunks_total + c) * BN_TX + tx];
+            }
+            const int i = sg_ * L + col;
+            if (c0 < c1) {
+                dbeta[i] = b;
+                dgamma[i] = g;
+                const float n = sg_ == 0 ? (float)B : (float)(R - B);
+                dbv = -(__ldg(gamma + i) * __ldg(rstd + i)) * g * (x / n);
+            }
         }
+        s_db[ty * (BN_TX + 1) + tx] = dbv;
     }
-}
-
-__global__ void db_combine_kernel(const float* __restrict__ db_seg, int L, float* __restrict__ db) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < L) db[c] = db_seg[c] + db_seg[L + c];
+    __syncthreads();
+    if (db && ty == 0 && col < L) db[col] = s_db[tx] + s_db[(BN_TX + 1) + tx];
 }
 
 // pass 2 (in place): dH = gamma*rstd * (g - dbeta/n - xhat*dgamma/n)
@@ -361,11 +400,14 @@ static int ew_blocks(size_t total) {
 
 using namespace dssm;
 
+// workspace = [ticket counters, one per 32-column strip | chunk partials]
+static inline size_t bn_ticket_bytes(int L) { return align_up((size_t)cdiv(L, BN_TX) * sizeof(int), 256); }
+
 extern "C" size_t dssm_bn_workspace_bytes(int32_t R, int32_t L) {
     if (R <= 0 || L <= 0) return 0;
     // worst case split of R rows into two segments adds one chunk
     const size_t chunks = (size_t)bn_chunks_of(R) + 2;
-    return align_up((3 * chunks + 2) * (size_t)L * sizeof(float), 256);
+    return bn_ticket_bytes(L) + align_up(3 * chunks * (size_t)L * sizeof(float), 256);
 }
 
 extern "C" int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, int32_t on_train, int32_t update_ema,
@@ -378,17 +420,19 @@ extern "C" int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, 
     cudaStream_t st = (cudaStream_t)stream;
     const int cr = bn_chunk_rows(R, B);
     const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
-    float* part = (float*)workspace;
+    BnFinalize fin{gamma, beta, ema_mean, ema_var, mean, var, rstd, scale, shift, eps, ema_decay, update_ema, nq};
     if (on_train) {
-        DSSM_REQUIRE(workspace && workspace_bytes >= (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
+        DSSM_REQUIRE(workspace && workspace_bytes >= bn_ticket_bytes(L) + (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
                      "dssm_bn_forward: workspace too small");
+        int* tickets = (int*)workspace;
+        float* part = (float*)((char*)workspace + bn_ticket_bytes(L));
         dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
-        bn_stats_kernel<<<grid, block, 0, st>>>(X, R, L, B, part, nt, cr);
+        bn_stats_kernel<<<grid, block, 0, st>>>(X, R, L, B, part, nt, cr, tickets, fin);
         LAUNCH_CHECK("bn_stats");
+    } else {
+        bn_eval_affine_kernel<<<cdiv(2 * L, 256), 256, 0, st>>>(L, fin);
+        LAUNCH_CHECK("bn_eval_affine");
     }
-    bn_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, on_train, update_ema, gamma, beta, ema_mean,
-                                                         ema_var, eps, ema_decay, mean, var, rstd, scale, shift);
-    LAUNCH_CHECK("bn_finalize");
     return DSSM_OK;
 }
 
@@ -419,19 +463,14 @@ extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_
     DSSM_REQUIRE(B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
     const int cr = bn_chunk_rows(R, B);
     const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
-    DSSM_REQUIRE(workspace && workspace_bytes >= ((size_t)3 * nt + 2) * L * sizeof(float), DSSM_ERR_WORKSPACE,
+    DSSM_REQUIRE(workspace && workspace_bytes >= bn_ticket_bytes(L) + (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
                  "dssm_bn_act_backward: workspace too small");
-    float* part = (float*)workspace;
-    float* db_seg = db ? part + (size_t)3 * nt * L : nullptr;
-    dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY);
-    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr);
+    int* tickets = (int*)workspace;
+    float* part = (float*)((char*)workspace + bn_ticket_bytes(L));
+    dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY_BWD);
+    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr, tickets, gamma, dgamma,
+                                                  dbeta, db);
     LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<cdiv(2 * L, 8), 256, 0, st>>>(part, nt, nq, L, B, R, gamma, rstd, dgamma, dbeta, db_seg);
-    LAUNCH_CHECK("bn_bwd_finalize");
-    if (db) {
-        db_combine_kernel<<<cdiv(L, 128), 128, 0, st>>>(db_seg, L, db);
-        LAUNCH_CHECK("db_combine");
-    }
     if (L % 4 == 0 && aligned16(dA) && aligned16(H) && aligned16(gamma) && aligned16(mean) && aligned16(rstd) && aligned16(scale) &&
         aligned16(shift) && aligned16(dgamma) && aligned16(dbeta)) {
         dim3 grid(cdiv(R, EW4_ROWS), cdiv(L / 4, 128));

@@ -130,6 +130,178 @@ cos_softmax_loss_kernel(const float* __restrict__ Hin, const float* __restrict__
     }
 }
 
+// 128-bit variant for L % 4 == 0, L <= 128*NV: the same arithmetic with every row held as NV float4 per lane and
+// CL_DB doc rows in flight per warp (loads and the 2*CL_DB shuffle reductions of a batch are independent chains), so
+// a warp's latency is ~(1+NEG)/CL_DB round trips instead of ~4*(1+NEG).  B warps is all the parallelism a batch
+// offers (7 warps per SM at B = 1024): the kernel is latency-bound, not bandwidth-bound.
+template <int NV>
+__global__ void __launch_bounds__(CL_WARPS * 32)
+cos_softmax_loss_v4_kernel(const float4* __restrict__ Hin, const float4* __restrict__ scale, const float4* __restrict__ shift,
+                           int act, float4* __restrict__ Y, int B, int NEG, int L4, float gamma, float loss_eps, float inv_denom,
+                           float* __restrict__ query_norm_single, float* __restrict__ doc_norm,
+                           float* __restrict__ cos_sim_raw, float* __restrict__ cos_sim, float* __restrict__ prob,
+                           float* __restrict__ loss_terms, float4* __restrict__ dY) {
+    constexpr int DB = 8 / NV;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int K1 = NEG + 1;
+    float* s_dot = smem + (size_t)w * 3 * K1;
+    float* s_dn = s_dot + K1;
+    float* s_c = s_dn + K1;
+    const int j = blockIdx.x * CL_WARPS + w;
+    if (j >= B) return;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = Hin ? Hin : Y;
+    const bool affine = Hin && scale;
+    auto doc_row = [&](int k) { return (k == 0) ? (size_t)(B + j) : (size_t)(2 * B) + (size_t)j * NEG + (k - 1); };
+    auto embed = [&](float4 x, float4 sc, float4 sh) {
+        if (affine) { x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w); }
+        if (Hin) { x.x = act_fwd(x.x, act); x.y = act_fwd(x.y, act); x.z = act_fwd(x.z, act); x.w = act_fwd(x.w, act); }
+        return x;
+    };
+    // query row (BN instance 0) and the doc instance's affine in registers
+    float4 qv[NV], scd[NV], shd[NV];
+    float qq = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c = lane + 32 * v;
+        qv[v] = z4; scd[v] = z4; shd[v] = z4;
+        if (c < L4) {
+            float4 sc = z4, sh = z4;
+            if (affine) { sc = __ldg(scale + c); sh = __ldg(shift + c); scd[v] = __ldg(scale + L4 + c); shd[v] = __ldg(shift + L4 + c); }
+            qv[v] = embed(src[(size_t)j * L4 + c], sc, sh);
+            if (Hin) Y[(size_t)j * L4 + c] = qv[v];
+            qq = fmaf(qv[v].x, qv[v].x, qq); qq = fmaf(qv[v].y, qv[v].y, qq); qq = fmaf(qv[v].z, qv[v].z, qq); qq = fmaf(qv[v].w, qv[v].w, qq);
+        }
+    }
+    qq = warp_sum(qq);
+    const float qn = sqrtf(qq);
+    // dots and doc norms, DB rows per round
+    for (int k0 = 0; k0 < K1; k0 += DB) {
+        float4 d[DB][NV];
+#pragma unroll
+        for (int u = 0; u < DB; ++u)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c = lane + 32 * v;
+                d[u][v] = (k0 + u < K1 && c < L4) ? src[doc_row(k0 + u) * L4 + c] : z4;
+            }
+        float dd[DB], dq[DB];
+#pragma unroll
+        for (int u = 0; u < DB; ++u) {
+            dd[u] = 0.f; dq[u] = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c = lane + 32 * v;
+                if (k0 + u < K1 && c < L4) {
+                    const float4 x = embed(d[u][v], scd[v], shd[v]);
+                    if (Hin) Y[doc_row(k0 + u) * L4 + c] = x;
+                    dd[u] = fmaf(x.x, x.x, dd[u]); dd[u] = fmaf(x.y, x.y, dd[u]); dd[u] = fmaf(x.z, x.z, dd[u]); dd[u] = fmaf(x.w, x.w, dd[u]);
+                    dq[u] = fmaf(x.x, qv[v].x, dq[u]); dq[u] = fmaf(x.y, qv[v].y, dq[u]); dq[u] = fmaf(x.z, qv[v].z, dq[u]); dq[u] = fmaf(x.w, qv[v].w, dq[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < DB; ++u) {
+                dd[u] += __shfl_xor_sync(0xffffffffu, dd[u], o);
+                dq[u] += __shfl_xor_sync(0xffffffffu, dq[u], o);
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < DB; ++u)
+                if (k0 + u < K1) { s_dot[k0 + u] = dq[u]; s_dn[k0 + u] = sqrtf(dd[u]); }
+        }
+    }
+    __syncwarp();
+    // softmax over the 1+NEG logits (lanes stride over k); s_c holds raw until the coefficients replace it
+    float mx = -INFINITY, any_nan = 0.f;
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_dot[k] / (qn * s_dn[k]);  // tf.truediv, no epsilon: 0/0 = NaN
+        s_c[k] = raw;
+        mx = fmaxf(mx, raw * gamma);
+        if (raw != raw) any_nan = 1.f;
+    }
+    mx = warp_max(mx);
+    any_nan = warp_sum(any_nan);
+    float se = 0.f;
+    for (int k = lane; k < K1; k += 32) se += expf(s_c[k] * gamma - mx);
+    se = warp_sum(se);
+    __syncwarp();
+    const float p0 = expf(s_c[0] * gamma - mx) / se;
+    // NaN anywhere in the group poisons the softmax exactly as in TF; fmaxf drops NaNs, so re-inject
+    const float poison = any_nan > 0.f ? NAN : 0.f;
+    const float wgt = p0 / (p0 + loss_eps);
+    float sum_c_raw = 0.f;
+    __syncwarp();
+    for (int k = lane; k < K1; k += 32) {
+        const float raw = s_c[k];
+        const float logit = raw * gamma;
+        const float p = expf(logit - mx) / se + poison;
+        if (cos_sim_raw) cos_sim_raw[(size_t)k * B + j] = raw;
+        if (doc_norm) doc_norm[(size_t)k * B + j] = s_dn[k];
+        if (cos_sim) cos_sim[(size_t)j * K1 + k] = logit;
+        if (prob) prob[(size_t)j * K1 + k] = p;
+        // dLoss/dcos_k = gamma * w * (p_k - [k==0]) / denom
+        const float dcos = gamma * (wgt * (p - (k == 0 ? 1.f : 0.f)) * inv_denom);
+        sum_c_raw = fmaf(dcos, raw, sum_c_raw);
+        // row coefficients of the backward: dd_k = a_k * q - b_k * d_k,  dq = sum_k a_k * d_k - qcoef * q
+        const float dn = s_dn[k];
+        const float inv_qd = 1.f / (qn * dn);
+        s_dot[k] = dcos * inv_qd;                            // a_k
+        s_c[k] = dcos * raw / (dn * dn);                     // b_k
+    }
+    sum_c_raw = warp_sum(sum_c_raw);
+    if (lane == 0) {
+        if (query_norm_single) query_norm_single[j] = qn;
+        loss_terms[j] = -logf(p0 + poison + loss_eps);
+    }
+    if (!dY) return;
+    __syncwarp();
+    const float qcoef = sum_c_raw / (qn * qn);
+    float4 dqa[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dqa[v] = z4;
+    for (int k0 = 0; k0 < K1; k0 += DB) {
+        float4 d[DB][NV];
+#pragma unroll
+        for (int u = 0; u < DB; ++u)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c = lane + 32 * v;
+                d[u][v] = (k0 + u < K1 && c < L4) ? Y[doc_row(k0 + u) * L4 + c] : z4;
+            }
+#pragma unroll
+        for (int u = 0; u < DB; ++u) {
+            if (k0 + u >= K1) continue;
+            const float a = s_dot[k0 + u], b = s_c[k0 + u];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c = lane + 32 * v;
+                if (c < L4) {
+                    const float4 x = d[u][v];
+                    float4 o;
+                    o.x = a * qv[v].x - b * x.x; o.y = a * qv[v].y - b * x.y; o.z = a * qv[v].z - b * x.z; o.w = a * qv[v].w - b * x.w;
+                    dY[doc_row(k0 + u) * L4 + c] = o;
+                    dqa[v].x = fmaf(a, x.x, dqa[v].x); dqa[v].y = fmaf(a, x.y, dqa[v].y);
+                    dqa[v].z = fmaf(a, x.z, dqa[v].z); dqa[v].w = fmaf(a, x.w, dqa[v].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c = lane + 32 * v;
+        if (c < L4) {
+            float4 o;
+            o.x = dqa[v].x - qcoef * qv[v].x; o.y = dqa[v].y - qcoef * qv[v].y;
+            o.z = dqa[v].z - qcoef * qv[v].z; o.w = dqa[v].w - qcoef * qv[v].w;
+            dY[(size_t)j * L4 + c] = o;
+        }
+    }
+}
+
 // loss = sum_j terms[j] * inv_denom, single block, fixed tree
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ terms, int B, float inv_denom,
                                                             float* __restrict__ loss) {
@@ -189,9 +361,19 @@ static int cos_softmax_loss_impl(const float* Hin, const float* scale, const flo
     DSSM_REQUIRE(smem <= 48 * 1024, DSSM_ERR_BAD_SHAPE, "dssm_cos_softmax_loss: NEG=%d too large", NEG);
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_denom = loss_div_bs ? 1.0f / (float)B : 1.0f;
-    cos_softmax_loss_kernel<<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(Hin, scale, shift, act, Y, B, NEG, L, gamma, loss_eps, inv_denom,
-                                                                            query_norm_single, doc_norm, cos_sim_raw,
-                                                                            cos_sim, prob, loss_terms, dY);
+    const bool v4 = L % 4 == 0 && L <= 256 && aligned16(Y) && (!Hin || aligned16(Hin)) && (!scale || (aligned16(scale) && aligned16(shift))) &&
+                    (!dY || aligned16(dY));
+#define CL_V4_ARGS (const float4*)Hin, (const float4*)scale, (const float4*)shift, act, (float4*)Y, B, NEG, L / 4, gamma, loss_eps, inv_denom, \
+                   query_norm_single, doc_norm, cos_sim_raw, cos_sim, prob, loss_terms, (float4*)dY
+    if (v4 && L <= 128)
+        cos_softmax_loss_v4_kernel<1><<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(CL_V4_ARGS);
+    else if (v4)
+        cos_softmax_loss_v4_kernel<2><<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(CL_V4_ARGS);
+    else
+        cos_softmax_loss_kernel<<<cdiv(B, CL_WARPS), CL_WARPS * 32, smem, st>>>(Hin, scale, shift, act, Y, B, NEG, L, gamma, loss_eps, inv_denom,
+                                                                                query_norm_single, doc_norm, cos_sim_raw,
+                                                                                cos_sim, prob, loss_terms, dY);
+#undef CL_V4_ARGS
     LAUNCH_CHECK("cos_softmax_loss");
     if (loss) {
         loss_reduce_kernel<<<1, 1024, 0, st>>>(loss_terms, B, inv_denom, loss);

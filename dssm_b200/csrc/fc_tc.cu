@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Warp-specialised variant for the K-major contractions whose B operand is a pre-built weight image (forward, dX):
-//   warps 0-3  producers: stage the activation tile (register prefetch one k-block ahead, BN scale/shift from shared
-//              memory, hi/lo split, swizzled store), fence.proxy.async, arrive on full_a[stage]          (128 arrivals)
-//   warp 4     lane 0 issues the MMAs as soon as full_a / full_b of a stage have completed, tcgen05.commit -> empty
-//   warp 5     lane 0 streams the B image tiles with cp.async.bulk -> full_b (complete_tx), waiting on empty for reuse
-//   all 8 warps drain TMEM at the end.
+//   warps 0-7  producers: stage the activation tile (register ring WS_PF k-blocks ahead, BN scale/shift from shared
+//              memory, hi/lo split, swizzled store), fence.proxy.async, arrive on full_a[stage]          (256 arrivals)
+//   warp 8     lane 0 issues the MMAs as soon as full_a / full_b of a stage have completed, tcgen05.commit -> empty
+//   warp 9     lane 0 streams the B image tiles with cp.async.bulk -> full_b (complete_tx), waiting on empty for reuse
+//   warps 0-7 drain TMEM at the end.
 // No CTA-wide barrier inside the main loop: producers run up to STAGES k-blocks ahead of the tensor core.
 constexpr int WS_MAX_K = 512;  // scale/shift of both BN instances live in shared memory (8 KB static next to 217 KB dynamic)
 
@@ -342,6 +342,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int WS_PF = 4;                       // k-blocks of activation loads in flight per producer thread
 constexpr int WS_PRODUCERS = 256;             // warps 0-7
 constexpr int WS_THREADS = WS_PRODUCERS + 64;  // + warp 8 (MMA issuer) + warp 9 (B image loader)
 
@@ -410,43 +411,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
             rowp[i] = g.A + (size_t)(okm[i] ? m : 0) * g.K + c * 4;
             off[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
         }
-        float4 cur[4], nxt[4];
+        // register ring, WS_PF k-blocks of loads in flight per thread (64 KB per CTA): one k-block ahead leaves most of
+        // the L2 round trip exposed, because converting a k-block takes far less time than fetching one
+        float4 buf[WS_PF][4];
         auto load4 = [&](int kb, float4 (&q)[4]) {
-            const bool okk = kb * BK + c * 4 < g.K;
+            const bool okk = kb < nkb && kb * BK + c * 4 < g.K;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 q[i] = (okm[i] && okk) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        load4(0, cur);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % STAGES, use = kb / STAGES;
-            if (kb + 1 < nkb) load4(kb + 1, nxt);
-            if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
-            char* a_hi = smem + st * stage_bytes;
-            char* a_lo = a_hi + A_TILE_BYTES;
-            const int k = kb * BK + c * 4;
-            const bool okk = k < g.K;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 v = cur[i];
-                if (okm[i] && okk) {  // padding stays exactly zero
-                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg[i]][k]);
-                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg[i]][k]);
-                    v.x = act_t<ACT>(fmaf(v.x, sc.x, sh.x));
-                    v.y = act_t<ACT>(fmaf(v.y, sc.y, sh.y));
-                    v.z = act_t<ACT>(fmaf(v.z, sc.z, sh.z));
-                    v.w = act_t<ACT>(fmaf(v.w, sc.w, sh.w));
+        for (int j = 0; j < WS_PF; ++j) load4(j, buf[j]);
+        for (int kb0 = 0; kb0 < nkb; kb0 += WS_PF) {
+#pragma unroll
+            for (int j = 0; j < WS_PF; ++j) {
+                const int kb = kb0 + j;
+                if (kb >= nkb) break;
+                const int st = kb % STAGES, use = kb / STAGES;
+                if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
+                char* a_hi = smem + st * stage_bytes;
+                char* a_lo = a_hi + A_TILE_BYTES;
+                const int k = kb * BK + c * 4;
+                const bool okk = k < g.K;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 v = buf[j][i];
+                    if (okm[i] && okk) {  // padding stays exactly zero
+                        const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg[i]][k]);
+                        const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg[i]][k]);
+                        v.x = act_t<ACT>(fmaf(v.x, sc.x, sh.x));
+                        v.y = act_t<ACT>(fmaf(v.y, sc.y, sh.y));
+                        v.z = act_t<ACT>(fmaf(v.z, sc.z, sh.z));
+                        v.w = act_t<ACT>(fmaf(v.w, sc.w, sh.w));
+                    }
+                    float4 hi, lo;
+                    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+                    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+                    *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
+                    *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
                 }
-                float4 hi, lo;
-                hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-                lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
-                *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
-                *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
+                fence_proxy_async();  // this thread's generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&full_a[st]);
+                load4(kb + WS_PF, buf[j]);  // refill the slot just consumed
             }
-            fence_proxy_async();  // this thread's generic-proxy writes -> visible to the tensor core
-            mbar_arrive(&full_a[st]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer

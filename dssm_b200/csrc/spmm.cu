@@ -12,6 +12,7 @@ namespace dssm {
 constexpr int GATHER_UNROLL = 4;
 constexpr int SPMM_THREADS = 256;
 constexpr int CSC_CHUNK = 128;  // entries of one column handled by one warp in the dW1 gather
+constexpr int ITEM_GRAB = 4;       // single-item columns claimed per atomic in the gather
 constexpr int MAX_W1_CHUNKS = 64;  // column chunks the gather can be issued in (data-parallel comm overlap)
 
 // acc[k] += sum_{p in [s,e)} val[p] * src4[idx[p]*L4 + lane + 32k]   (sequential in p)
@@ -296,7 +297,7 @@ csc_scan_local_kernel(const int* __restrict__ colcnt, int D, int* __restrict__ c
 __global__ void __launch_bounds__(SCAN_THREADS)
 csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, int* __restrict__ colptr,
                     int* __restrict__ cursor, int* __restrict__ itemptr, const int* __restrict__ colcnt,
-                    int4* __restrict__ item_rec) {
+                    int4* __restrict__ item_rec, int* __restrict__ n_heavy, int* __restrict__ heavy_list) {
     __shared__ int2 red[SCAN_THREADS / 32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     int oa = 0, ob = 0;
@@ -324,6 +325,10 @@ csc_scan_add_kernel(int D, int n_blocks, const int2* __restrict__ block_totals, 
             const int ni = items_of(cnt);
             for (int i = 0; i < ni; ++i)
                 item_rec[first + i] = make_int4(col, p + i * CSC_CHUNK, min(p + cnt, p + (i + 1) * CSC_CHUNK), ni);
+            if (ni > 1) {  // items of multi-item columns also go on the "heavy" list the full-range gather starts with
+                const int hb = atomicAdd(n_heavy, ni);
+                for (int i = 0; i < ni; ++i) heavy_list[hb + i] = first + i;
+            }
         }
     }
     if ((int)blockIdx.x == n_blocks - 1 && t == 0) {
@@ -355,6 +360,7 @@ struct AdamW1 {
     const float* beta_pow;  // device: beta1^t, beta2^t
     float lr, b1, b2, eps;
     const int* colcnt;      // columns without entries get the g = 0 update (dense-Adam semantics of the reference)
+    int absent_done;        // ... unless dssm_spmm_bwd_adam_absent already gave it to them
 };
 
 template <int NCH>
@@ -389,7 +395,8 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
                     float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4,
-                    int col_begin, int col_end, AdamW1 adam) {
+                    int col_begin, int col_end, AdamW1 adam, int* __restrict__ heavy_ctl /* {count, cursor} */,
+                    const int* __restrict__ heavy_list /* NULL: plain item order */) {
     extern __shared__ float4 ring_smem[];
     float lr_t = 0.f;
     if (FUSE_ADAM) {
@@ -403,15 +410,27 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
     // items of the columns [col_begin, col_end): a contiguous item range (chunked gather for comm overlap)
     const int item_lo = __ldg(itemptr + col_begin), n_items = __ldg(itemptr + col_end);
     (void)wpb; (void)stride; (void)D;
-    // dynamic work distribution: item costs range from 0 to CSC_CHUNK gathered rows, a static round-robin leaves
-    // half of the SMs idle behind the stragglers (ncu: sm__cycles_active.avg = 48 % of elapsed)
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = item_lo + atomicAdd(next_item, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
+    // Dynamic work distribution (item costs range from 1 to CSC_CHUNK gathered rows; a static round-robin leaves half of
+    // the SMs idle behind the stragglers).  Two refinements: (1) the full-range gather first drains the "heavy" list --
+    // the items of multi-item columns, ~CSC_CHUNK rows each, half of all entries under a Zipf vocabulary -- so that
+    // their long dependent chains start at t = 0 instead of wherever column order put them; (2) the remaining
+    // single-item columns are claimed ITEM_GRAB at a time: one same-address atomic per item caps the kernel at the
+    // L2's serialised atomic rate.
+    auto process = [&](int item, bool skip_multi) {
         const int4 rec = __ldg(item_rec + item);
         const int c = rec.x, s = rec.y, e = rec.z, n_col_items = rec.w;
+        if (skip_multi && n_col_items > 1) return;
+        if (FUSE_ADAM) {
+            // start pulling this column's w / m / v rows from HBM into L2 now: the Adam loads at the end of the item then
+            // cost an L2 hit instead of a DRAM round trip that nothing else in the warp could hide
+            const int row_bytes = L4 * 16;
+            const int lines = (row_bytes + 127) / 128;
+            for (int i = lane; i < 3 * lines; i += 32) {
+                const int arr = i / lines, ln = i - arr * lines;
+                const char* base = reinterpret_cast<const char*>((arr == 0 ? adam.w : arr == 1 ? adam.m : adam.v) + (size_t)c * L4);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 128));
+            }
+        }
         float4 acc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -468,8 +487,26 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                 if (lane == 0) done[c] = 0;  // leave the counters clean for the next step
             }
         }
+    };
+    if (heavy_list) {
+        const int nh = __ldg(heavy_ctl);
+        for (;;) {
+            int h = 0;
+            if (lane == 0) h = atomicAdd(heavy_ctl + 1, 1);
+            h = __shfl_sync(0xffffffffu, h, 0);
+            if (h >= nh) break;
+            process(__ldg(heavy_list + h), false);
+        }
     }
-    if (FUSE_ADAM) {
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = item_lo + atomicAdd(next_item, ITEM_GRAB);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_items) break;
+        const int end = min(base + ITEM_GRAB, n_items);
+        for (int item = base; item < end; ++item) process(item, heavy_list != nullptr);
+    }
+    if (FUSE_ADAM && !adam.absent_done) {
         // columns absent from the batch: zero gradient, but m, v decay and w keeps moving on its momentum
         float4 zero[NCH];
 #pragma unroll
@@ -480,8 +517,35 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
     }
 }
 
+// The g = 0 Adam update of the W1 rows whose column does not occur in the batch.  It needs the column histogram only,
+// and neither the forward (which reads just the rows of occurring columns) nor the backward touches those rows, so
+// the train step runs it on the side stream right after the CSC build, under the dense layers.
+template <int NCH>
+__global__ void __launch_bounds__(SPMM_THREADS)
+adam_absent_columns_kernel(int D, int L4, AdamW1 adam) {
+    const float b1p = __ldg(adam.beta_pow), b2p = __ldg(adam.beta_pow + 1);
+    const float lr_t = adam.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float4 zero[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) zero[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < D; c += gridDim.x * wpb)
+        if (__ldg(adam.colcnt + c) == 0) adam_row<NCH>(adam, c, L4, lane, zero, lr_t);
+}
+
+template <int NCH>
+static void launch_adam_absent(int D, int L1, const AdamW1& ad, cudaStream_t st) {
+    // two blocks per SM: the kernel has the whole dense stack to hide under, but the blocks it keeps resident take
+    // thread slots from the main stream's kernels (1024-thread BN blocks, 320-thread GEMM CTAs); 16 warps x 9 float4
+    // loads in flight per lane are still ~70 KB per SM, enough to stream
+    int blocks = sm_count() * 2;
+    const int need = cdiv(D, SPMM_THREADS / 32);
+    if (blocks > need) blocks = need;
+    adam_absent_columns_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(D, L1 / 4, ad);
+}
+
 struct CscWorkspace {
-    int *colcnt, *done, *next_item, *colptr, *cursor, *itemptr, *csc_row;
+    int *colcnt, *done, *next_item, *heavy_ctl, *colptr, *cursor, *itemptr, *csc_row, *heavy_list;
     int2* block_totals;
     int4* item_rec;
     float* csc_val;
@@ -495,12 +559,14 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.colcnt = a.take<int>(D + 1);   // colcnt and done are contiguous: one memset clears both
     w.done = a.take<int>(D + 1);
     w.next_item = a.take<int>(MAX_W1_CHUNKS);  // one work counter per column chunk; cleared together with colcnt / done
+    w.heavy_ctl = a.take<int>(2);              // {heavy items, cursor}, cleared with them
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
     w.itemptr = a.take<int>(D + 1);
     w.block_totals = a.take<int2>((size_t)(D + SCAN_TILE - 1) / SCAN_TILE + 1);
     w.csc_row = a.take<int>((size_t)max_nnz);
     w.csc_val = a.take<float>((size_t)max_nnz);
+    w.heavy_list = a.take<int>(2 * (size_t)(max_nnz / CSC_CHUNK) + 2);  // items of columns with > CSC_CHUNK entries
     const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
     w.item_rec = a.take<int4>(max_items);
     w.partial = a.take<float>(max_items * (size_t)L1);
@@ -531,7 +597,7 @@ static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, 
         }
     }
 #define DW_ARGS w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val, (const float4*)dH, (float4*)dW, (float4*)w.partial, w.done, \
-                w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad
+                w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad, w.heavy_ctl, (col_begin == 0 && col_end == D) ? w.heavy_list : nullptr
     if (async && adam) dw_gather_v4_kernel<NCH, true, true><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
     else if (async) dw_gather_v4_kernel<NCH, true, false><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
     else if (adam) dw_gather_v4_kernel<NCH, false, true><<<blocks, SPMM_THREADS, 0, st>>>(DW_ARGS);
@@ -635,7 +701,7 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
     LAUNCH_CHECK("csc_scan_local");
     csc_scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(D, scan_blocks, w.block_totals, w.colptr, w.cursor, w.itemptr,
-                                                              w.colcnt, w.item_rec);
+                                                              w.colcnt, w.item_rec, w.heavy_ctl, w.heavy_list);
     LAUNCH_CHECK("csc_scan_add");
     const int wpb = SPMM_THREADS / 32;
     int blocks = cdiv(R, wpb);
@@ -667,19 +733,38 @@ extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t R, int32_t D, int
 // Gather fused with TF-Adam on W1 (single-GPU train step): the gradient rows are consumed in registers, W1 / m / v are
 // updated in place (absent columns get the g = 0 update), dW1 is NOT produced.  beta_pow is read, not advanced.
 extern "C" int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, float* W1, float* m1, float* v1,
-                                     const float* beta_pow, float lr, float beta1, float beta2, float eps, void* workspace,
-                                     size_t workspace_bytes, dssm_stream_t stream) {
+                                     const float* beta_pow, float lr, float beta1, float beta2, float eps, int32_t absent_done,
+                                     void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(dH && W1 && m1 && v1 && beta_pow, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_adam: null pointer");
     DSSM_REQUIRE(L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_dw_adam: bad L1");
     DSSM_REQUIRE(aligned16(dH) && aligned16(W1) && aligned16(m1) && aligned16(v1), DSSM_ERR_BAD_ALIGN, "dssm_spmm_bwd_dw_adam: buffers must be 16-byte aligned");
     CscWorkspace w;
     int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
     if (rc != DSSM_OK) return rc;
-    AdamW1 ad{(float4*)W1, (float4*)m1, (float4*)v1, beta_pow, lr, beta1, beta2, eps, nullptr};
+    AdamW1 ad{(float4*)W1, (float4*)m1, (float4*)v1, beta_pow, lr, beta1, beta2, eps, nullptr, absent_done != 0};
     const int nch = cdiv(L1 / 4, 32);
     const bool async = (size_t)R * L1 * sizeof(float) <= ((size_t)32 << 20);
     DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, nullptr, D, L1, 0, D, 0, async, &ad, (cudaStream_t)stream));
     LAUNCH_CHECK("dw_gather_adam");
+    return DSSM_OK;
+}
+
+// First half of the fused W1 update: TF-Adam with g = 0 on the rows of W1 / m1 / v1 whose column is absent from the
+// batch whose CSC is in the workspace.  Order it after dssm_spmm_bwd_csc_build; it may run concurrently with
+// dssm_spmm_fwd and the dense layers of the same step (disjoint rows); follow with dssm_spmm_bwd_dw_adam(absent_done=1).
+extern "C" int dssm_spmm_bwd_adam_absent(int32_t D, int32_t L1, float* W1, float* m1, float* v1, const float* beta_pow, float lr,
+                                         float beta1, float beta2, float eps, void* workspace, size_t workspace_bytes,
+                                         dssm_stream_t stream) {
+    DSSM_REQUIRE(W1 && m1 && v1 && beta_pow, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_adam_absent: null pointer");
+    DSSM_REQUIRE(D > 0 && L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_adam_absent: bad shape");
+    DSSM_REQUIRE(aligned16(W1) && aligned16(m1) && aligned16(v1), DSSM_ERR_BAD_ALIGN, "dssm_spmm_bwd_adam_absent: buffers must be 16-byte aligned");
+    CscWorkspace w;
+    int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
+    if (rc != DSSM_OK) return rc;
+    AdamW1 ad{(float4*)W1, (float4*)m1, (float4*)v1, beta_pow, lr, beta1, beta2, eps, w.colcnt, 0};
+    const int nch = cdiv(L1 / 4, 32);
+    DISPATCH_NCH(nch, launch_adam_absent<N_>(D, L1, ad, (cudaStream_t)stream));
+    LAUNCH_CHECK("adam_absent_columns");
     return DSSM_OK;
 }
 

@@ -28,19 +28,46 @@ extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int3
 extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, dssm_stream_t stream);
 namespace dssm {
 
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+
 // phase boundaries of one profiled step (dssm_tower_profile_step)
 enum { PH_START = 0, PH_SPMM_FWD, PH_DENSE_FWD, PH_COSLOSS, PH_DENSE_BWD, PH_CSC_BUILD, PH_DW_GATHER, PH_B1, PH_ADAM, PH_COUNT };
 struct PhaseTimer {
     cudaEvent_t ev[PH_COUNT];
     cudaStream_t st;
     bool on;
+    bool serial;  // true: side-stream work and the W1 Adam fusion are folded back so every phase is timed alone
+    std::vector<cudaEvent_t>* fine_ev;  // optional per-call timeline (dssm_tower_profile_timeline)
+    std::vector<std::string>* fine_name;
+    unsigned long long* stamps;  // device: when set, labels are %globaltimer stamps by a 1-thread kernel (graph-capturable)
     void mark(int i) {
-        if (on) cudaEventRecord(ev[i], st);
+        if (on && !stamps) cudaEventRecord(ev[i], st);
+    }
+    void markf(const std::string& name) {
+        if (!on || !fine_name) return;
+        if (stamps) {
+            stamp_kernel<<<1, 1, 0, st>>>(stamps + fine_name->size());
+            fine_name->push_back(name);
+            return;
+        }
+        if (!fine_ev) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        fine_ev->push_back(e);
+        fine_name->push_back(name);
     }
 };
 static thread_local PhaseTimer* g_timer = nullptr;
 static inline void mark(int i) {
     if (g_timer) g_timer->mark(i);
+}
+static inline void markf(const std::string& name) {
+    if (g_timer) g_timer->markf(name);
 }
 
 }  // namespace dssm
@@ -313,6 +340,9 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     t->ws_bytes = workspace_bytes;
     t->max_nnz = max_nnz;
     tower_carve(t, t->ws, max_nnz);
+    // the reduction kernels keep self-resetting ticket counters at the head of their workspaces
+    CUDA_TRY(cudaMemset(t->bn_ws, 0, t->bn_ws_bytes));
+    CUDA_TRY(cudaMemset(t->dw_ws, 0, t->dw_ws_bytes));
     if (!t->side) {
         CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
@@ -336,10 +366,11 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     const dssm_config& c = t->cfg;
     const int n = t->n_layers, R = t->R, B = t->B;
     mark(PH_START);
+    markf("start");
     t->csc_forked = false;
     t->img_forked = false;
     const bool tc = c.gemm_mode == DSSM_GEMM_TC_3XTF32 && n >= 2;
-    const bool timing = g_timer && g_timer->on;
+    const bool timing = g_timer && g_timer->on && g_timer->serial;
     const bool train = want_grad && on_train;
     const bool fork_csc = train && t->L[1] % 4 == 0 && t->L[1] <= 1024 && !timing;
     cudaStream_t main_st = (cudaStream_t)s;
@@ -364,15 +395,25 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         CUDA_TRY(cudaEventRecord(t->ev_img, t->side));
         t->img_forked = true;
     }
+    TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
     if (fork_csc) {
+        // forked AFTER the FC1 SpMM: that kernel is bandwidth-bound and loses what the CSC build takes from it, while the
+        // dense layers that follow are latency-bound and leave most of the memory system idle
+        CUDA_TRY(cudaEventRecord(t->ev_fork, main_st));
+        CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
         TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1],
                                     (t->grads_p && !t->fuse_w1_adam) ? t->G_("W1") : nullptr, t->sp_ws, t->sp_ws_bytes,
                                     (dssm_stream_t)t->side));
+        if (t->fuse_w1_adam) {  // the rows of W1 this batch does not touch take their Adam step under the dense layers
+            const int64_t wo = t->params[t->find(t->params, "W1")].off;
+            TRY(dssm_spmm_bwd_adam_absent(t->D, t->L[1], t->params_p + wo, t->m_p + wo, t->v_p + wo, t->beta_pow_p, c.learning_rate,
+                                          c.beta1, c.beta2, c.adam_eps, t->sp_ws, t->sp_ws_bytes, (dssm_stream_t)t->side));
+        }
         CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
         t->csc_forked = true;
     }
-    TRY(dssm_spmm_fwd(indptr, indices, values, R, t->D, t->P_("W1"), t->P_("b1"), t->L[1], t->h[1], s));
     mark(PH_SPMM_FWD);
+    markf("spmm_fwd");
     if (tc && timing) TRY(build_images());  // profiled step: serial, accounted to the dense forward
     if (t->img_forked) CUDA_TRY(cudaStreamWaitEvent(main_st, t->ev_img, 0));
     for (int l = 1; l <= n; ++l) {
@@ -382,6 +423,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
                                 t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
                                 c.bn_eps, c.ema_decay, t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l],
                                 t->bn_shift[l], t->bn_ws, t->bn_ws_bytes, s));
+            markf("bn_fwd" + ls);
         }
         const float* sc = c.use_bn ? t->bn_scale[l] : nullptr;
         const float* sh = c.use_bn ? t->bn_shift[l] : nullptr;
@@ -394,6 +436,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
                 TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
                                 t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));
             }
+            markf("fc_fwd" + ns);
         } else {
             mark(PH_DENSE_FWD);
             // last layer: BN + activation fused into the cosine / loss kernel, which also writes the embeddings Y
@@ -401,6 +444,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
                                             t->qnorm, t->dnorm, t->cos_raw, t->cos_sim, t->prob, t->loss_terms, t->loss,
                                             want_grad ? t->dh[n] : nullptr, s));
             mark(PH_COSLOSS);
+            markf("cos_loss");
         }
     }
     t->cur_indptr = indptr; t->cur_indices = indices; t->cur_values = values;
@@ -428,28 +472,33 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, nullptr, nullptr, nullptr, nullptr, nullptr,
                                      nullptr, nullptr, nullptr, nullptr, 0, s));
         }
+        markf("bn_bwd" + ls);
         if (l > 1) {
             const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
             const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
             // under BN the bias gradient came out of dssm_bn_act_backward; without BN it is the column sum of dH
             TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
                                c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
+            markf("fc_dw" + ls);
             if (c.gemm_mode == DSSM_GEMM_TC_3XTF32 && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
                 TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], s));
             } else {
                 TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, t->fc_ws,
                                    t->fc_ws_bytes, s));
             }
+            markf("fc_dx" + ls);
         } else {
             mark(PH_DENSE_BWD);
             if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
                 CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join, 0));
                 t->csc_forked = false;
+                mark(PH_CSC_BUILD);  // overlapped profile: time the main stream waited for the side stream
+                markf("join_side_stream");
                 if (w1_mode == 0 && t->fuse_w1_adam) {
                     const int wi = t->find(t->params, "W1");
                     const int64_t wo = t->params[wi].off;
                     TRY(dssm_spmm_bwd_dw_adam(t->dh[1], R, t->D, t->L[1], t->params_p + wo, t->m_p + wo, t->v_p + wo, t->beta_pow_p,
-                                              c.learning_rate, c.beta1, c.beta2, c.adam_eps, t->sp_ws, t->sp_ws_bytes, s));
+                                              c.learning_rate, c.beta1, c.beta2, c.adam_eps, 1, t->sp_ws, t->sp_ws_bytes, s));
                 } else if (w1_mode == 0) {
                     TRY(dssm_spmm_bwd_dw_range(t->dh[1], R, t->D, t->L[1], t->G_("W1"), 0, t->D, 0, t->sp_ws, t->sp_ws_bytes, s));
                 }
@@ -458,13 +507,14 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
                 TRY(dssm_spmm_bwd_csc_build(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->L[1], t->G_("W1"), t->sp_ws,
                                             t->sp_ws_bytes, s));
             } else {
-                if (g_timer && g_timer->on) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];
+                if (g_timer && g_timer->on && g_timer->serial) g_spmm_bwd_mid_event = g_timer->ev[PH_CSC_BUILD];
                 const int rc = dssm_spmm_bwd_dw(t->cur_indptr, t->cur_indices, t->cur_values, R, t->D, t->dh[1], t->L[1],
                                                 t->G_("W1"), 0, t->sp_ws, t->sp_ws_bytes, s);
                 g_spmm_bwd_mid_event = nullptr;
                 TRY(rc);
             }
             mark(PH_DW_GATHER);
+            markf("dw1_gather");
             if (!c.use_bn) TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
             mark(PH_B1);
         }
@@ -562,7 +612,7 @@ static int tower_step_impl(dssm_tower* t, const int32_t* indptr, const int32_t* 
     // single-GPU step: W1's Adam update rides on the dW1 gather (the CSC is built beside the forward) unless the
     // step is being phase-profiled or FC1's width rules out the vector kernels
     const int wi = t->find(t->params, "W1");
-    const bool fuse = t->L[1] % 4 == 0 && t->L[1] <= 1024 && !(g_timer && g_timer->on) && t->params[wi].off == 0;
+    const bool fuse = t->L[1] % 4 == 0 && t->L[1] <= 1024 && !(g_timer && g_timer->on && g_timer->serial) && t->params[wi].off == 0;
     t->fuse_w1_adam = fuse;
     int rc = tower_forward_impl(t, indptr, indices, values, 1, 1, true, s);
     if (rc == DSSM_OK) rc = tower_backward_impl(t, s);
@@ -692,19 +742,24 @@ extern "C" int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_ind
 
 extern "C" int64_t dssm_tower_launch_count(const dssm_tower* t) { return t ? t->launches : -1; }
 
-extern "C" int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream) {
+static int profile_step_impl(dssm_tower* t, float* host_phase_ms, bool serial, dssm_stream_t stream,
+                             std::vector<cudaEvent_t>* fine_ev = nullptr, std::vector<std::string>* fine_name = nullptr) {
     DSSM_REQUIRE(t && t->bound && host_phase_ms, DSSM_ERR_STATE, "dssm_tower_profile_step: tower not bound / null output");
     DSSM_REQUIRE(t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_profile_step: optimizer buffers not bound");
     PhaseTimer pt;
     pt.st = (cudaStream_t)stream;
     pt.on = true;
+    pt.serial = serial;
+    pt.fine_ev = fine_ev;
+    pt.fine_name = fine_name;
+    pt.stamps = nullptr;
     for (int i = 0; i < PH_COUNT; ++i) CUDA_TRY(cudaEventCreate(&pt.ev[i]));
     g_timer = &pt;
     int rc;
     {
         LaunchScope ls(t);
         rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
-        if (rc == DSSM_OK) mark(PH_ADAM);
+        if (rc == DSSM_OK) { mark(PH_ADAM); markf("adam_rest"); }
     }
     g_timer = nullptr;
     if (rc == DSSM_OK) {
@@ -719,4 +774,70 @@ extern "C" int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm
         }
     for (int i = 0; i < PH_COUNT; ++i) cudaEventDestroy(pt.ev[i]);
     return rc;
+}
+
+extern "C" int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream) {
+    return profile_step_impl(t, host_phase_ms, true, stream);
+}
+
+// Same events around the step as it really runs (side stream, fused W1 Adam): phase i is then main-stream time between
+// its boundaries, "csc_build" becomes the time the main stream waited at the join, "adam" the non-W1 parameters.
+extern "C" int dssm_tower_profile_step_overlapped(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream) {
+    return profile_step_impl(t, host_phase_ms, false, stream);
+}
+
+// Timeline of the step as it really runs, INSIDE a CUDA graph: the step is captured with a 1-thread %globaltimer stamp
+// after every call on the main stream (each costs a graph node, ~1.5 us), replayed three times, and the stamps of the
+// last replay are read back.  names receives the labels joined by ';', ms[i] the time between label i-1 and label i
+// (ms[0] = 0); *n_out their count.  Profiling helper: allocates its own small stamp buffer and synchronises.
+extern "C" int dssm_tower_profile_timeline(dssm_tower* t, char* names, int32_t names_cap, float* ms, int32_t max_n, int32_t* n_out,
+                                           dssm_stream_t stream) {
+    DSSM_REQUIRE(names && ms && n_out && names_cap > 0 && max_n > 0, DSSM_ERR_BAD_ARG, "dssm_tower_profile_timeline: null output");
+    DSSM_REQUIRE(t && t->bound && t->grads_p && t->m_p && t->v_p && t->beta_pow_p, DSSM_ERR_STATE, "dssm_tower_profile_timeline: tower not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSSM_REQUIRE(st != nullptr, DSSM_ERR_BAD_ARG, "dssm_tower_profile_timeline: needs a non-default stream");
+    constexpr int MAX_STAMPS = 128;
+    unsigned long long* d_stamps = nullptr;
+    CUDA_TRY(cudaMalloc(&d_stamps, MAX_STAMPS * sizeof(unsigned long long)));
+    std::vector<std::string> nm;
+    PhaseTimer pt;
+    pt.st = st;
+    pt.on = true;
+    pt.serial = false;
+    pt.fine_ev = nullptr;
+    pt.fine_name = &nm;
+    pt.stamps = d_stamps;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    int rc = DSSM_OK;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        g_timer = &pt;
+        rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
+        if (rc == DSSM_OK) markf("adam_rest");
+        g_timer = nullptr;
+        e = cudaStreamEndCapture(st, &g);
+    }
+    if (rc == DSSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ge, g, 0);
+    for (int i = 0; rc == DSSM_OK && e == cudaSuccess && i < 3; ++i) e = cudaGraphLaunch(ge, st);
+    if (rc == DSSM_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    int n = 0;
+    if (rc == DSSM_OK && e == cudaSuccess) {
+        std::vector<unsigned long long> h(MAX_STAMPS);
+        e = cudaMemcpy(h.data(), d_stamps, MAX_STAMPS * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        std::string joined;
+        for (size_t i = 0; e == cudaSuccess && i < nm.size() && n < max_n && n < MAX_STAMPS; ++i, ++n) {
+            ms[n] = i ? (float)((double)(h[i] - h[i - 1]) * 1e-6) : 0.f;
+            if (i) joined += ";";
+            joined += nm[i];
+        }
+        snprintf(names, (size_t)names_cap, "%s", joined.c_str());
+    }
+    if (ge) cudaGraphExecDestroy(ge);
+    if (g) cudaGraphDestroy(g);
+    cudaFree(d_stamps);
+    *n_out = n;
+    if (rc != DSSM_OK) return rc;
+    if (e != cudaSuccess) return fail(DSSM_ERR_CUDA, "dssm_tower_profile_timeline: %s", cudaGetErrorString(e));
+    return DSSM_OK;
 }

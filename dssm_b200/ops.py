@@ -37,6 +37,11 @@ def _ws(nbytes: int, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def _ws_zero(nbytes: int, device):
+    """Workspaces that start with self-resetting ticket counters (BN reductions, split-K dW) must begin zeroed."""
+    return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
 @dataclass
 class DeviceCSR:
     """Stacked batch on the device (int32 indptr/indices, fp32 values)."""
@@ -163,7 +168,7 @@ def bn_forward(X, B: int, state: BNState, on_train: bool, update_ema: bool = Tru
     state.mean/var/rstd/scale/shift (and moves the shadows when training)."""
     _require_cuda(X)
     R, L = X.shape
-    ws = _ws(lib.dssm_bn_workspace_bytes(R, L), X.device)
+    ws = _ws_zero(lib.dssm_bn_workspace_bytes(R, L), X.device)
     check(lib.dssm_bn_forward(ptr(X), R, L, B, int(on_train), int(update_ema), ptr(state.gamma), ptr(state.beta),
                               ptr(state.ema_mean), ptr(state.ema_var), eps, decay, ptr(state.mean), ptr(state.var),
                               ptr(state.rstd), ptr(state.scale), ptr(state.shift), ptr(ws), ws.numel(), stream_ptr()))
@@ -199,7 +204,7 @@ def bn_act_backward(dA, H, B: int, act, state: Optional[BNState], want_db: bool 
         return (None, None, None) if want_db else (None, None)
     dgamma, dbeta = _f32((2, L), H.device), _f32((2, L), H.device)
     db = _f32((L,), H.device) if want_db else None
-    ws = _ws(lib.dssm_bn_workspace_bytes(R, L), H.device)
+    ws = _ws_zero(lib.dssm_bn_workspace_bytes(R, L), H.device)
     check(lib.dssm_bn_act_backward(ptr(dA), ptr(H), R, L, B, ACT[act], ptr(state.gamma), ptr(state.mean), ptr(state.rstd),
                                    ptr(state.scale), ptr(state.shift), ptr(dgamma), ptr(dbeta), ptr(db), ptr(ws), ws.numel(),
                                    stream_ptr()))

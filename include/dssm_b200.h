@@ -114,11 +114,17 @@ int dssm_spmm_bwd_dw_range(const float* dH, int32_t R, int32_t D, int32_t L1, fl
                            int32_t chunk, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 
 /* The gather fused with tf.train.AdamOptimizer on weight1 (new_dssm.py:217) for the single-GPU step: after
- * dssm_spmm_bwd_csc_build(dW1 = NULL), every dW1 row is consumed in registers and W1 / m / v are updated in place
- * (columns absent from the batch get the zero-gradient update: dense-Adam semantics); dW1 itself is not produced. */
+ * dssm_spmm_bwd_csc_build(dW1 = NULL), every dW1 row is consumed in registers and W1 / m / v are updated in place;
+ * dW1 itself is not produced.  Columns absent from the batch get the zero-gradient update (dense-Adam semantics),
+ * either here (absent_done = 0) or, earlier and off the critical path, by dssm_spmm_bwd_adam_absent (absent_done = 1):
+ * that call needs only the CSC's column histogram and touches rows neither dssm_spmm_fwd nor the backward of the
+ * same batch reads, so it may run on another stream beside them, ordered after dssm_spmm_bwd_csc_build. */
 int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, float* W1, float* m1, float* v1,
-                          const float* beta_pow, float lr, float beta1, float beta2, float eps, void* workspace,
-                          size_t workspace_bytes, dssm_stream_t stream);
+                          const float* beta_pow, float lr, float beta1, float beta2, float eps, int32_t absent_done,
+                          void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+int dssm_spmm_bwd_adam_absent(int32_t D, int32_t L1, float* W1, float* m1, float* v1, const float* beta_pow, float lr,
+                              float beta1, float beta2, float eps, void* workspace, size_t workspace_bytes,
+                              dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
@@ -129,6 +135,9 @@ int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, flo
  *   on_train == 0: mean/var = shadows                                       (new_dssm.py:85-86)
  *   out: mean,var,rstd = rsqrt(var+eps), scale = gamma*rstd, shift = beta - mean*scale  (:87)
  * The normalised tensor itself is not written: consumers apply act(x*scale+shift) on load.
+ * workspace (dssm_bn_workspace_bytes, shared by dssm_bn_forward and dssm_bn_act_backward): must be ZERO-FILLED once
+ * before its first use -- it starts with the ticket counters of the "last block finalizes" reductions, which every
+ * call leaves at zero again.  Calls sharing a workspace must be ordered (same stream).
  */
 size_t dssm_bn_workspace_bytes(int32_t R, int32_t L);
 int dssm_bn_forward(const float* X, int32_t R, int32_t L, int32_t B, int32_t on_train, int32_t update_ema,
@@ -265,7 +274,8 @@ size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nnz);
 int32_t dssm_tower_num_tensors(const dssm_tower* t, int32_t kind);
 int dssm_tower_tensor_info(const dssm_tower* t, int32_t kind, int32_t index, char* name, int32_t name_cap,
                            int64_t* offset_floats, int64_t* rows, int64_t* cols);
-/* beta_pow: 2 floats (device) initialised by the caller to {beta1, beta2}. */
+/* beta_pow: 2 floats (device) initialised by the caller to {beta1, beta2}.  bind clears the ticket counters inside
+ * the workspace (a synchronous cudaMemset: call it outside stream capture). */
 int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float* m, float* v, float* ema, float* beta_pow,
                     void* workspace, size_t workspace_bytes, int64_t max_nnz);
 /* sess.run(loss / embeddings, feed_dict=pull_batch(on_train, ...)) -- new_dssm.py:276-285,
@@ -311,6 +321,14 @@ int64_t dssm_tower_launch_count(const dssm_tower* t);
 /* One un-graphed train step on the staging CSR with CUDA events between the phases; synchronises.
  * host_phase_ms[8] = {FC1 SpMM fwd, dense fwd (BN+FC), cosine/loss, dense bwd, CSC build, dW1 gather, db1, Adam}. */
 int dssm_tower_profile_step(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream);
+/* The same events around the step as it really runs (side stream, W1 Adam fused into the gather): "CSC build" is then
+ * the time the main stream waited for the side stream at the join, "Adam" the parameters behind W1. */
+int dssm_tower_profile_step_overlapped(dssm_tower* t, float* host_phase_ms, dssm_stream_t stream);
+/* Timeline of that step inside a CUDA graph: a 1-thread %globaltimer stamp after every call on the main stream (each
+ * stamp is a graph node, ~1.5 us).  names <- labels joined by ';', ms[i] <- milliseconds between label i-1 and label i
+ * (ms[0] = 0), *n_out <- number of labels.  Needs a non-default stream; allocates a 1 KB stamp buffer; synchronises. */
+int dssm_tower_profile_timeline(dssm_tower* t, char* names, int32_t names_cap, float* ms, int32_t max_n, int32_t* n_out,
+                                dssm_stream_t stream);
 
 #ifdef __cplusplus
 }
