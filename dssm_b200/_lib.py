@@ -117,6 +117,8 @@ SIGNATURES = {
     "dssm_tower_capture_graph": (C.c_int, [_p, _p]),
     "dssm_tower_staging": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "dssm_tower_train_step_staged": (C.c_int, [_p, _p]),
+    "dssm_tower_train_step_host_async": (C.c_int64, [_p, _p, _p, _p, _i64, _p, _p]),
+    "dssm_tower_feed_wait": (C.c_int, [_p, _i64]),
     "dssm_tower_launch_count": (_i64, [_p]),
     "dssm_tower_profile_step": (C.c_int, [_p, C.POINTER(C.c_float), _p]),
     "dssm_tower_profile_step_overlapped": (C.c_int, [_p, C.POINTER(C.c_float), _p]),

@@ -110,6 +110,13 @@ struct dssm_tower {
     // The per-batch CSC of X depends only on the input batch: it is built on a side stream, forked at the start
     // of the training forward and joined right before the dW1 gather (also inside graph capture).
     cudaStream_t side;
+    // pipelined host feed (dssm_tower_train_step_host_async): upload buffers k%2 filled on the copy stream
+    cudaStream_t copy;
+    cudaEvent_t ev_up_ready[2], ev_up_free[2], ev_step_done[2];
+    int32_t* up_indptr[2];
+    int32_t* up_indices[2];
+    float* up_values[2];
+    int64_t feed_k;
     cudaEvent_t ev_fork, ev_join;
     bool csc_forked;
     bool fuse_w1_adam;  // set for the duration of tower_step_impl: gather + Adam on W1 in one kernel, dW1 never stored
@@ -138,6 +145,11 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     t->st_indptr = a.take<int32_t>(R + 1);
     t->st_indices = a.take<int32_t>((size_t)max_nnz);
     t->st_values = a.take<float>((size_t)max_nnz);
+    for (int b = 0; b < 2; ++b) {
+        t->up_indptr[b] = a.take<int32_t>(R + 1);
+        t->up_indices[b] = a.take<int32_t>((size_t)max_nnz);
+        t->up_values[b] = a.take<float>((size_t)max_nnz);
+    }
     for (int l = 1; l <= n; ++l) {
         t->h[l] = a.take<float>((size_t)R * t->L[l]);
         reg("h" + std::to_string(l), t->h[l], R, t->L[l]);
@@ -255,6 +267,9 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->graph_dp_exec = nullptr;
     t->launches_per_dp = 0;
     t->side = nullptr;
+    t->copy = nullptr;
+    for (int b = 0; b < 2; ++b) t->ev_up_ready[b] = t->ev_up_free[b] = t->ev_step_done[b] = nullptr;
+    t->feed_k = 0;
     t->ev_fork = nullptr;
     t->ev_join = nullptr;
     t->ev_img = nullptr;
@@ -277,6 +292,12 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (t->ev_join) cudaEventDestroy(t->ev_join);
     if (t->ev_img) cudaEventDestroy(t->ev_img);
     if (t->side) cudaStreamDestroy(t->side);
+    for (int b = 0; b < 2; ++b) {
+        if (t->ev_up_ready[b]) cudaEventDestroy(t->ev_up_ready[b]);
+        if (t->ev_up_free[b]) cudaEventDestroy(t->ev_up_free[b]);
+        if (t->ev_step_done[b]) cudaEventDestroy(t->ev_step_done[b]);
+    }
+    if (t->copy) cudaStreamDestroy(t->copy);
     delete t;
 }
 
@@ -348,7 +369,14 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_img, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&t->ev_up_ready[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&t->ev_up_free[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&t->ev_step_done[b], cudaEventDisableTiming));
+        }
     }
+    t->feed_k = 0;
     t->csc_forked = false;
     t->bound = true;
     t->fwd_train_done = false;
@@ -737,6 +765,59 @@ extern "C" int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_ind
         CUDA_TRY(cudaMemcpyAsync(host_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
+    return DSSM_OK;
+}
+
+// Pipelined host feed, step k (k counts calls since bind): the CSR travels pinned host -> upload buffer k%2 on the
+// tower's copy stream while the previous step still computes; on `stream` it is then moved into the staging CSR (the
+// train-step graph reads fixed addresses), the step runs, and the loss goes to host_loss.  Nothing synchronises here.
+extern "C" int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                                    const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream) {
+    if (!(t && t->bound)) { fail(DSSM_ERR_STATE, "dssm_tower_train_step_host_async: tower not bound"); return -1; }
+    if (!(host_indptr && host_indices && host_values)) { fail(DSSM_ERR_BAD_ARG, "dssm_tower_train_step_host_async: null CSR pointer"); return -1; }
+    if (!(nnz >= 0 && nnz <= t->max_nnz)) {
+        fail(DSSM_ERR_WORKSPACE, "dssm_tower_train_step_host_async: nnz %lld exceeds bound max_nnz %lld", (long long)nnz, (long long)t->max_nnz);
+        return -1;
+    }
+    if (!(host_indptr[0] == 0 && host_indptr[t->R] == nnz)) {
+        fail(DSSM_ERR_BAD_SHAPE, "dssm_tower_train_step_host_async: batch must have exactly (2+NEG)*query_BS = %d rows and indptr[R] == nnz", t->R);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t k = t->feed_k;
+    const int b = (int)(k & 1);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    if (k >= 2) ok(cudaStreamWaitEvent(t->copy, t->ev_up_free[b], 0));  // step k-2 has drained this upload buffer
+    ok(cudaMemcpyAsync(t->up_indptr[b], host_indptr, (size_t)(t->R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, t->copy));
+    if (nnz > 0) {
+        ok(cudaMemcpyAsync(t->up_indices[b], host_indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, t->copy));
+        ok(cudaMemcpyAsync(t->up_values[b], host_values, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, t->copy));
+    }
+    ok(cudaEventRecord(t->ev_up_ready[b], t->copy));
+    ok(cudaStreamWaitEvent(st, t->ev_up_ready[b], 0));
+    ok(cudaMemcpyAsync(t->st_indptr, t->up_indptr[b], (size_t)(t->R + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (nnz > 0) {
+        ok(cudaMemcpyAsync(t->st_indices, t->up_indices[b], (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        ok(cudaMemcpyAsync(t->st_values, t->up_values[b], (size_t)nnz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    ok(cudaEventRecord(t->ev_up_free[b], st));
+    if (e != cudaSuccess) { fail(DSSM_ERR_CUDA, "dssm_tower_train_step_host_async: %s", cudaGetErrorString(e)); return -1; }
+    if (dssm_tower_train_step_staged(t, stream) != DSSM_OK) return -1;
+    if (host_loss) ok(cudaMemcpyAsync(host_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    ok(cudaEventRecord(t->ev_step_done[b], st));
+    if (e != cudaSuccess) { fail(DSSM_ERR_CUDA, "dssm_tower_train_step_host_async: %s", cudaGetErrorString(e)); return -1; }
+    t->feed_k = k + 1;
+    return k;
+}
+
+// Blocks until pipelined step `step` (a value returned by dssm_tower_train_step_host_async; only the last two are
+// waitable) has finished: its host_loss is valid and its host CSR buffers may be reused.
+extern "C" int dssm_tower_feed_wait(dssm_tower* t, int64_t step) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_feed_wait: tower not bound");
+    DSSM_REQUIRE(step >= 0 && step < t->feed_k && step >= t->feed_k - 2, DSSM_ERR_BAD_ARG,
+                 "dssm_tower_feed_wait: step %lld is not one of the last two issued (%lld issued)", (long long)step, (long long)t->feed_k);
+    CUDA_TRY(cudaEventSynchronize(t->ev_step_done[step & 1]));
     return DSSM_OK;
 }
 

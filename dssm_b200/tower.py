@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT, GEMM, check, lib, ptr, stream_ptr
+from ._lib import ACT, GEMM, DssmError, check, last_error, lib, ptr, stream_ptr
 from .batch import DOC_NEG_BATCH, DOC_POS_BATCH, ON_TRAIN, QUERY_BATCH, StackedBatch, stack_feed
 from .config import Config
 from .ops import DeviceCSR
@@ -312,6 +312,42 @@ class DSSMTower:
         hl = ptr(self._host_loss) if read_loss else None
         check(lib.dssm_tower_train_step_host(self._h, ptr(indptr), ptr(indices), ptr(values), nnz, hl, stream_ptr()))
         return float(self._host_loss[0]) if read_loss else None
+
+    # pipelined host feed: step k's upload overlaps step k-1's compute (include/dssm_b200.h)
+    def train_step_host_async(self, pinned) -> int:
+        """Issue one step from pinned HOST buffers without synchronising; returns its step id.  Keep at most two steps
+        in flight: call feed_loss(step) (or feed_wait) on the one before last before issuing another."""
+        indptr, indices, values, nnz = pinned
+        if getattr(self, "_loss_slots", None) is None:
+            self._loss_slots = torch.zeros(2, dtype=torch.float32).pin_memory()
+        k_next = getattr(self, "_feed_next", 0)
+        slot = C.c_void_p(self._loss_slots.data_ptr() + 4 * (k_next & 1))
+        k = lib.dssm_tower_train_step_host_async(self._h, ptr(indptr), ptr(indices), ptr(values), nnz, slot, stream_ptr())
+        if k < 0:
+            raise DssmError(int(k), last_error())
+        self._feed_next = k + 1
+        return int(k)
+
+    def feed_wait(self, step: int) -> None:
+        check(lib.dssm_tower_feed_wait(self._h, step))
+
+    def feed_loss(self, step: int) -> float:
+        """Loss of pipelined step `step` (blocks until that step is done)."""
+        self.feed_wait(step)
+        return float(self._loss_slots[step & 1])
+
+    def train_epoch_host(self, pinned_batches) -> list:
+        """The reference's inner training loop (new_dssm.py:261-269) over host batches with the double-buffered feed;
+        returns every step's loss."""
+        losses, prev = [], None
+        for pb in pinned_batches:
+            k = self.train_step_host_async(pb)
+            if prev is not None:
+                losses.append(self.feed_loss(prev))
+            prev = k
+        if prev is not None:
+            losses.append(self.feed_loss(prev))
+        return losses
 
     PHASES = ("spmm_fwd", "dense_fwd", "cos_loss", "dense_bwd", "csc_build", "dw_gather", "db1", "adam")
 

@@ -316,6 +316,15 @@ int dssm_tower_capture_graph(dssm_tower* t, dssm_stream_t stream);
 int dssm_tower_staging(dssm_tower* t, int32_t** indptr, int32_t** indices, float** values);
 /* Run one train step on whatever is in the staging CSR (graph replay when captured). */
 int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream);
+/* Pipelined host feed (the reference's training loop holds host batches: pull_batch, utils/utils.py:45-61, fed one
+ * per sess.run, new_dssm.py:261-269).  dssm_tower_train_step_host_async uploads step k's CSR from PINNED host memory
+ * on the tower's own copy stream into upload buffer k%2 while step k-1 still computes, then runs the step on `stream`
+ * and copies the loss to host_loss (pinned, one slot per in-flight step); it never synchronises and returns k (< 0 on
+ * error, see dssm_last_error).  dssm_tower_feed_wait(k) blocks until step k is done: its loss is valid and its host
+ * buffers may be reused.  Only the last two issued steps are waitable; keep at most two in flight. */
+int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                         const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream);
+int dssm_tower_feed_wait(dssm_tower* t, int64_t step);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dssm_tower_launch_count(const dssm_tower* t);
 /* One un-graphed train step on the staging CSR with CUDA events between the phases; synchronises.

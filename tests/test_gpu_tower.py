@@ -205,6 +205,36 @@ def test_host_step_graph_and_sess_run_shim():
     assert_update_close({"W2": d.export_params()["W2"]}, {"W2": e.export_params()["W2"]}, params, conf.use_bn, "run('train_step')")
 
 
+def test_pipelined_host_feed_matches_synchronous_host_steps():
+    """dssm_tower_train_step_host_async (upload of step k+1 on the copy stream under step k, losses read one step late)
+    trains exactly like the synchronous host path: same losses step by step, same parameters; a batch reusing the pinned
+    buffers of step k-2 is safe; a malformed batch is rejected before anything is enqueued."""
+    from dssm_b200 import Config, DSSMTower
+    from dssm_b200._lib import DssmError
+    from dssm_b200.synthetic import init_params, make_batch
+
+    conf = Config(TRIGRAM_D=21128, query_BS=100, NEG=4, layers=(300, 300, 128))
+    batches = [make_batch(conf, seed=s, lam_query=12, lam_doc=24) for s in range(3)]
+    params = init_params(conf, 0)
+    mx = max(b.nnz for b in batches)
+    a, b_ = DSSMTower(conf, max_nnz=mx, params=params), DSSMTower(conf, max_nnz=mx, params=params)
+    a.capture_graph()
+    b_.capture_graph()
+    seq = [batches[i % 3] for i in range(7)]
+    ref = [a.train_step_host(a.pin(bt)) for bt in seq]
+    pinned = [b_.pin(bt) for bt in batches]  # 3 pinned buffers cycled over 7 steps
+    got = b_.train_epoch_host([pinned[i % 3] for i in range(7)])
+    assert len(got) == len(ref)
+    for i, (x, y) in enumerate(zip(ref, got)):
+        assert abs(x - y) <= 2e-4 * abs(x), f"step {i}: {x} vs {y}"
+    assert_update_close(b_.export_params(), a.export_params(), params, conf.use_bn, "pipelined feed", l2_tol=2e-2)
+    with pytest.raises(DssmError):
+        b_.feed_wait(0)  # only the last two steps are waitable
+    ip, ix, vl, nnz = pinned[0]
+    with pytest.raises(DssmError):
+        b_.train_step_host_async((ip, ix, vl, nnz - 1))  # indptr[R] != nnz
+
+
 def test_wrong_batch_shape_is_rejected():
     from dssm_b200 import Config, DSSMTower
     from dssm_b200.synthetic import make_batch
