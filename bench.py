@@ -201,10 +201,10 @@ def run_ours(args):
     max_nnz = max(b.nnz for b in batches)
     mean_nnz = float(np.mean([b.nnz for b in batches]))
     params = init_params(conf, 0)
-    tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params)
+    tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params, symmetric=(world > 1 and args.dp_comm == "nvlink"))
     dev_batches = [tower.to_device(b) for b in batches]
     pinned = [tower.pin(b) for b in batches]
-    dp = DataParallelTower(tower) if world > 1 else None
+    dp = DataParallelTower(tower, comm=args.dp_comm) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -383,7 +383,8 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": describe(conf, args.workload, world, {"mean_nnz_per_step_per_gpu": mean_nnz, "gemm_mode": conf.gemm_mode,
                                                                "distinct_batches": NB, "cuda_graph": True,
-                                                               "dp_w1_chunks": (dp.n_chunks if dp else None)}),
+                                                               "dp_w1_chunks": (dp.n_chunks if dp else None),
+                                                               "dp_comm": (args.dp_comm if dp else None)}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms, "last_loss": last_loss},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "retrieval": retrieval}
@@ -414,6 +415,9 @@ def main():
     ap.add_argument("--workload", default="C2", help="C1 | C2 | C3 | C4 | C4_NOBN (per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the secondary corpus top-k measurement")
+    ap.add_argument("--dp-comm", default="nvlink", choices=["nccl", "nvlink"],
+                    help="N>1: dW1 exchange by NCCL all-reduce (chunked, overlapped) or by the fused pull/Adam/push kernel over "
+                         "NVLink peer memory (csrc/nvlink.cu)")
     ap.add_argument("--gemm-mode", default="tc_3xtf32", choices=["fp32", "tc_3xtf32"],
                     help="dense-layer arithmetic: FFMA fp32 or tcgen05 3xTF32 (both hold the 1e-5 parity bar)")
     args = ap.parse_args()

@@ -95,3 +95,16 @@ __device__ __forceinline__ void red_add4(float* p, float4 v) {
 #endif
 
 }  // namespace dssm
+
+// float4 chunks per lane for a row of L floats handled by one warp: compile-time unrolled for 1..8 (L <= 1024)
+#define DISPATCH_NCH(nch, CALL)                       \
+    switch (nch) {                                    \
+        case 1: { constexpr int N_ = 1; CALL; } break; \
+        case 2: { constexpr int N_ = 2; CALL; } break; \
+        case 3: { constexpr int N_ = 3; CALL; } break; \
+        case 4: { constexpr int N_ = 4; CALL; } break; \
+        case 5: { constexpr int N_ = 5; CALL; } break; \
+        case 6: { constexpr int N_ = 6; CALL; } break; \
+        case 7: { constexpr int N_ = 7; CALL; } break; \
+        default: { constexpr int N_ = 8; CALL; } break; \
+    }

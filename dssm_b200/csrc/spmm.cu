@@ -616,18 +616,6 @@ static void launch_scatter(const int* indptr, const int* indices, const float* v
                                                                    R, L1 / 4);
 }
 
-#define DISPATCH_NCH(nch, CALL)                       \
-    switch (nch) {                                    \
-        case 1: { constexpr int N_ = 1; CALL; } break; \
-        case 2: { constexpr int N_ = 2; CALL; } break; \
-        case 3: { constexpr int N_ = 3; CALL; } break; \
-        case 4: { constexpr int N_ = 4; CALL; } break; \
-        case 5: { constexpr int N_ = 5; CALL; } break; \
-        case 6: { constexpr int N_ = 6; CALL; } break; \
-        case 7: { constexpr int N_ = 7; CALL; } break; \
-        default: { constexpr int N_ = 8; CALL; } break; \
-    }
-
 // set by the tower's profiling step: recorded between the CSC build and the gather kernel
 thread_local cudaEvent_t g_spmm_bwd_mid_event = nullptr;
 

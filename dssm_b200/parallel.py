@@ -50,9 +50,12 @@ class DataParallelTower:
     capture_graph() records the whole step -- kernels and collectives -- into one CUDA graph, so the ~60 launches
     cost no CPU time per step."""
 
-    def __init__(self, tower, group=None, n_chunks: int = 2):
+    def __init__(self, tower, group=None, n_chunks: int = 2, comm: str = "nccl"):
+        if comm not in ("nccl", "nvlink"):
+            raise ValueError("comm must be 'nccl' or 'nvlink'")
         self.tower = tower
         self.group = group
+        self.comm = comm
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_chunks = max(1, min(int(n_chunks), 64))
         off, rows, cols = tower._layout[0]["W1"]
@@ -63,9 +66,63 @@ class DataParallelTower:
         # identical starting parameters on every rank
         if self.world > 1:
             dist.broadcast(tower.params, src=0, group=group)
+        if comm == "nvlink" and self.world > 1:
+            try:
+                self._setup_nvlink()
+            except (RuntimeError, ImportError) as e:  # no peer mapping on this box / torch build: use NCCL, loudly
+                import sys
+
+                print(f"[dssm_b200] NVLink peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce",
+                      file=sys.stderr)
+                self.comm = "nccl"
+
+    # ---- NVLink peer-memory exchange of dW1 (csrc/nvlink.cu) --------------------------------------------------
+    def _setup_nvlink(self) -> None:
+        """Rendezvous of the tower's symmetric params / grads buffers: afterwards every rank holds device pointers to
+        every other rank's W1 and dW1.  Rank r owns the W1 rows [r*D/n, (r+1)*D/n): it alone reduces their gradient, runs
+        Adam on them and writes the result into all replicas."""
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = self.tower
+        if not (self.pipelined and getattr(t, "symmetric", False)):
+            raise ValueError("comm='nvlink' needs DSSMTower(..., symmetric=True) and an FC1 width that is a multiple of 4")
+        if self.world > 16:
+            raise ValueError("comm='nvlink' addresses at most 16 peers")
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(grp)
+        self._h_params = symm_mem.rendezvous(t.params, grp)
+        self._h_comm = symm_mem.rendezvous(t.comm, grp)
+        w1_off = t._layout[0]["W1"][0]  # 0 (checked by self.pipelined)
+        arr = C.c_void_p * self.world
+        self._peer_w = arr(*[int(p) + 4 * w1_off for p in self._h_params.buffer_ptrs])
+        self._peer_dw = arr(*[int(p) + 4 * w1_off for p in self._h_comm.buffer_ptrs])  # grads = comm[:P]
+        D = t.conf.TRIGRAM_D
+        per = (D + self.world - 1) // self.world
+        self.row_begin, self.row_end = min(self.rank * per, D), min((self.rank + 1) * per, D)
+
+    def _step_staged_nvlink(self) -> None:
+        from ._lib import check, lib, ptr, stream_ptr
+
+        t, c = self.tower, self.tower.conf
+        t.fwd_bwd_begin_staged()
+        # [grads beyond W1 | EMA shadows]: small, stays on NCCL; queued now so that it runs beside the dW1 gather
+        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        t.backward_w1(0, 1)  # this rank's dense dW1, in symmetric memory
+        self._h_comm.barrier(channel=0)  # every rank's dW1 is complete and visible
+        check(lib.dssm_w1_shard_reduce_adam(self._peer_dw, self._peer_w, self.world, self.rank, c.TRIGRAM_D, c.layers[0],
+                                            self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate,
+                                            c.beta1, c.beta2, c.adam_eps, stream_ptr()))
+        w_rest.wait()
+        t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
+        t.adam_advance()
+        self._h_params.barrier(channel=0)  # every owner's rows have landed in every replica of W1
 
     # ---- one step on the staging CSR -------------------------------------------------------------------
     def _step_staged(self) -> None:
+        if self.comm == "nvlink" and self.world > 1:
+            return self._step_staged_nvlink()
         t, n = self.tower, self.n_chunks
         t.fwd_bwd_begin_staged()
         if self.world == 1:

@@ -51,7 +51,7 @@ def _make_c_config(conf: Config) -> _lib.dssm_config:
 
 class DSSMTower:
     def __init__(self, conf: Config, max_nnz: int, device: Union[str, torch.device] = "cuda",
-                 params: Optional[Dict[str, np.ndarray]] = None, seed: int = 0):
+                 params: Optional[Dict[str, np.ndarray]] = None, seed: int = 0, symmetric: bool = False):
         if len(conf.layers) > _lib.MAX_LAYERS:
             raise ValueError("too many layers")
         self.conf = conf
@@ -66,10 +66,19 @@ class DSSMTower:
         self.E = lib.dssm_tower_ema_count(self._h)
         with torch.cuda.device(self.device):
             z = lambda n: torch.zeros(max(int(n), 4), dtype=torch.float32, device=self.device)
-            self.params, self.m, self.v = z(self.P), z(self.P), z(self.P)
+            self.symmetric = bool(symmetric)
+            if symmetric:
+                # parameters and gradients in peer-mappable (symmetric) memory: every rank of a process group can address
+                # them over NVLink once rendezvous'ed (DataParallelTower(comm="nvlink")); needs torch.distributed
+                import torch.distributed._symmetric_memory as symm_mem
+
+                zs = lambda n: symm_mem.empty(max(int(n), 4), dtype=torch.float32, device=self.device).zero_()
+            else:
+                zs = z
+            self.params, self.m, self.v = zs(self.P), z(self.P), z(self.P)
             # grads and the EMA shadows share one allocation so that data-parallel training exchanges
             # [small gradients | EMA] with a single collective (dssm_b200/parallel.py)
-            self.comm = z(self.P + max(self.E, 4))
+            self.comm = zs(self.P + max(self.E, 4))
             self.grads, self.ema = self.comm[:self.P], self.comm[self.P:self.P + max(self.E, 4)]
             self.beta_pow = torch.tensor([conf.beta1, conf.beta2], dtype=torch.float32, device=self.device)
             ws_bytes = lib.dssm_tower_workspace_bytes(self._h, self.max_nnz)

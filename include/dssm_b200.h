@@ -58,6 +58,7 @@ enum { DSSM_ACT_NONE = 0, DSSM_ACT_RELU = 1, DSSM_ACT_TANH = 2 };
 enum { DSSM_GEMM_FP32 = 0, DSSM_GEMM_TC_3XTF32 = 1 };
 
 #define DSSM_MAX_LAYERS 8
+#define DSSM_MAX_PEERS 16 /* ranks addressable by the NVLink peer-memory exchange */
 
 /* Hyper-parameters; names follow semantic_matching/dssm/config.py:19-28 and new_dssm.py:44. */
 typedef struct dssm_config {
@@ -125,6 +126,18 @@ int dssm_spmm_bwd_dw_adam(const float* dH, int32_t R, int32_t D, int32_t L1, flo
 int dssm_spmm_bwd_adam_absent(int32_t D, int32_t L1, float* W1, float* m1, float* v1, const float* beta_pow, float lr,
                               float beta1, float beta2, float eps, void* workspace, size_t workspace_bytes,
                               dssm_stream_t stream);
+
+/* Data-parallel exchange of dW1 over NVLink peer memory, fused with Adam (no reference counterpart; SURVEY 8e's
+ * reduce-scatter -> sharded Adam -> all-gather as one kernel).  peer_dW1[r] / peer_W1[r] (HOST arrays of n_ranks device
+ * pointers, r = rank order, entry `self` being this rank's own buffers) address every rank's dense dW1 [D,L1] and W1
+ * [D,L1]; they must be peer-mapped (e.g. torch symmetric memory).  For the rows [row_begin,row_end) this rank owns, the
+ * kernel pulls the gradient row from every rank, sums in rank order, divides by n_ranks, applies TF-Adam with the local
+ * m1, v1 (full-size [D,L1] buffers; only the owned rows are touched) and writes the new weight row into every rank's W1.
+ * Ordering is the caller's: a cross-device barrier after all ranks produced dW1, another after this call before W1 is
+ * read again.  beta_pow is read, not advanced. */
+int dssm_w1_shard_reduce_adam(const float* const* peer_dW1, float* const* peer_W1, int32_t n_ranks, int32_t self, int32_t D,
+                              int32_t L1, int32_t row_begin, int32_t row_end, float* m1, float* v1, const float* beta_pow,
+                              float lr, float beta1, float beta2, float eps, dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer

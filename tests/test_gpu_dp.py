@@ -1,6 +1,7 @@
 """Data-parallel training on real GPUs (needs >= 2; skipped otherwise): two NCCL ranks, each with its own query
 groups, pipelined gather/all-reduce/Adam (and its CUDA-graph form) against DPOracle (per-replica BN moments, mean
-gradient, one Adam step)."""
+gradient, one Adam step); the same with dW1 exchanged over NVLink peer memory (comm="nvlink": pull / Adam / push kernel
+between two symmetric-memory barriers) instead of NCCL."""
 import os
 import socket
 
@@ -32,7 +33,7 @@ def _join_all(ctx, seconds, what):
             pytest.fail(f"{what} did not finish in {seconds} s")
 
 
-def _worker(rank, world, port, out, use_graph):
+def _worker(rank, world, port, out, use_graph, comm="nccl"):
     import torch.distributed as dist
 
     from dssm_b200 import Config, DSSMTower
@@ -45,8 +46,9 @@ def _worker(rank, world, port, out, use_graph):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     conf = Config(TRIGRAM_D=21128, query_BS=100, NEG=4, layers=(300, 300, 128), gemm_mode="tc_3xtf32")
     batches = [make_batch(conf, seed=10 * s + rank, lam_query=12, lam_doc=24) for s in range(2)]
-    t = DSSMTower(conf, max_nnz=max(b.nnz for b in batches), device=f"cuda:{rank}", params=init_params(conf, 0))
-    dp = DataParallelTower(t, n_chunks=3)
+    t = DSSMTower(conf, max_nnz=max(b.nnz for b in batches), device=f"cuda:{rank}", params=init_params(conf, 0),
+                  symmetric=(comm == "nvlink"))
+    dp = DataParallelTower(t, n_chunks=3, comm=comm)
     losses = []
     if use_graph:
         # capture on a scratch copy of the state, then restore it so the comparison starts from the initial parameters
@@ -67,8 +69,8 @@ def _worker(rank, world, port, out, use_graph):
     os._exit(0)  # skip the NCCL destructor (can block with captured collectives)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_two_gpu_data_parallel_matches_dp_oracle(tmp_path, use_graph):
+@pytest.mark.parametrize("use_graph,comm", [(False, "nccl"), (True, "nccl"), (False, "nvlink"), (True, "nvlink")])
+def test_two_gpu_data_parallel_matches_dp_oracle(tmp_path, use_graph, comm):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -79,7 +81,7 @@ def test_two_gpu_data_parallel_matches_dp_oracle(tmp_path, use_graph):
     from tests.helpers import assert_close, assert_update_close, oracle_config
 
     out = str(tmp_path / "rank0.npz")
-    ctx = mp.spawn(_worker, args=(2, _free_port(), out, use_graph), nprocs=2, join=False)
+    ctx = mp.spawn(_worker, args=(2, _free_port(), out, use_graph, comm), nprocs=2, join=False)
     _join_all(ctx, 240, "data-parallel workers")
     got = np.load(out)
     conf = Config(TRIGRAM_D=21128, query_BS=100, NEG=4, layers=(300, 300, 128))
