@@ -253,38 +253,23 @@ def run_ours(args):
     value = conf.query_BS * world / (ms_per_step / 1e3)
 
     # ---- leg 2: end to end from HOST buffers through the public API ("e2e") ---------------------------
-    if world == 1:
-        # Double-buffered feed (dssm_tower_train_step_host_async): every step uploads ITS OWN CSR from pinned host memory
-        # (on the tower's copy stream, overlapping the previous step's kernels) and its loss is copied back to the host;
-        # the host reads each loss one step late so that it never drains the GPU queue.
-        in_flight = [None]
+    # Double-buffered feed (dssm_tower_train_step_host_async / DataParallelTower.train_step_host_async): every step uploads
+    # ITS OWN CSR from pinned host memory (on the tower's copy stream, overlapping the previous step's kernels), runs the
+    # step (N>1: the data-parallel one, exchange included) and copies its loss back to the host; the host reads each
+    # loss one step late so that it never drains the GPU queue.
+    step_async = tower.train_step_host_async if world == 1 else dp.train_step_host_async
+    in_flight = [None]
 
-        def e2e_step(i):
-            k = tower.train_step_host_async(pinned[i % NB])
-            loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
-            in_flight[0] = k
-            return loss
+    def e2e_step(i):
+        k = step_async(pinned[i % NB])
+        loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
+        in_flight[0] = k
+        return loss
 
-        def e2e_flush():
-            loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
-            in_flight[0] = None
-            return loss
-    else:
-        def e2e_flush():
-            return None
-
-        host_loss = torch.zeros(1).pin_memory()
-
-        def e2e_step(i):
-            ip, ix, vl, nnz = pinned[i % NB]
-            sip, six, svl = tower.staging_views()
-            sip.copy_(ip, non_blocking=True)
-            six[:nnz].copy_(ix, non_blocking=True)
-            svl[:nnz].copy_(vl, non_blocking=True)
-            loss = dp.train_step(None)  # runs on the staging CSR just uploaded
-            host_loss.copy_(loss.view(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return float(host_loss[0])
+    def e2e_flush():
+        loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
+        in_flight[0] = None
+        return loss
 
     for i in range(max(args.warmup, 1)):
         e2e_step(i)

@@ -768,19 +768,19 @@ extern "C" int dssm_tower_train_step_host(dssm_tower* t, const int32_t* host_ind
     return DSSM_OK;
 }
 
-// Pipelined host feed, step k (k counts calls since bind): the CSR travels pinned host -> upload buffer k%2 on the
+// Pipelined host feed, step k (k counts uploads since bind): the CSR travels pinned host -> upload buffer k%2 on the
 // tower's copy stream while the previous step still computes; on `stream` it is then moved into the staging CSR (the
-// train-step graph reads fixed addresses), the step runs, and the loss goes to host_loss.  Nothing synchronises here.
-extern "C" int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
-                                                    const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream) {
-    if (!(t && t->bound)) { fail(DSSM_ERR_STATE, "dssm_tower_train_step_host_async: tower not bound"); return -1; }
-    if (!(host_indptr && host_indices && host_values)) { fail(DSSM_ERR_BAD_ARG, "dssm_tower_train_step_host_async: null CSR pointer"); return -1; }
+// train-step graphs read fixed addresses).  Nothing synchronises here.
+extern "C" int64_t dssm_tower_feed_upload_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                                const float* host_values, int64_t nnz, dssm_stream_t stream) {
+    if (!(t && t->bound)) { fail(DSSM_ERR_STATE, "dssm_tower_feed_upload_async: tower not bound"); return -1; }
+    if (!(host_indptr && host_indices && host_values)) { fail(DSSM_ERR_BAD_ARG, "dssm_tower_feed_upload_async: null CSR pointer"); return -1; }
     if (!(nnz >= 0 && nnz <= t->max_nnz)) {
-        fail(DSSM_ERR_WORKSPACE, "dssm_tower_train_step_host_async: nnz %lld exceeds bound max_nnz %lld", (long long)nnz, (long long)t->max_nnz);
+        fail(DSSM_ERR_WORKSPACE, "dssm_tower_feed_upload_async: nnz %lld exceeds bound max_nnz %lld", (long long)nnz, (long long)t->max_nnz);
         return -1;
     }
     if (!(host_indptr[0] == 0 && host_indptr[t->R] == nnz)) {
-        fail(DSSM_ERR_BAD_SHAPE, "dssm_tower_train_step_host_async: batch must have exactly (2+NEG)*query_BS = %d rows and indptr[R] == nnz", t->R);
+        fail(DSSM_ERR_BAD_SHAPE, "dssm_tower_feed_upload_async: batch must have exactly (2+NEG)*query_BS = %d rows and indptr[R] == nnz", t->R);
         return -1;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -802,12 +802,30 @@ extern "C" int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t
         ok(cudaMemcpyAsync(t->st_values, t->up_values[b], (size_t)nnz * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     ok(cudaEventRecord(t->ev_up_free[b], st));
-    if (e != cudaSuccess) { fail(DSSM_ERR_CUDA, "dssm_tower_train_step_host_async: %s", cudaGetErrorString(e)); return -1; }
-    if (dssm_tower_train_step_staged(t, stream) != DSSM_OK) return -1;
-    if (host_loss) ok(cudaMemcpyAsync(host_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, st));
-    ok(cudaEventRecord(t->ev_step_done[b], st));
-    if (e != cudaSuccess) { fail(DSSM_ERR_CUDA, "dssm_tower_train_step_host_async: %s", cudaGetErrorString(e)); return -1; }
+    if (e != cudaSuccess) { fail(DSSM_ERR_CUDA, "dssm_tower_feed_upload_async: %s", cudaGetErrorString(e)); return -1; }
     t->feed_k = k + 1;
+    return k;
+}
+
+// Closes pipelined step `step` (the value dssm_tower_feed_upload_async returned) after the caller has enqueued the work
+// that consumes the staging CSR: copies the loss to host_loss (may be NULL) and records the step's completion event.
+extern "C" int dssm_tower_feed_step_done(dssm_tower* t, int64_t step, float* host_loss, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound, DSSM_ERR_STATE, "dssm_tower_feed_step_done: tower not bound");
+    DSSM_REQUIRE(step == t->feed_k - 1, DSSM_ERR_BAD_ARG, "dssm_tower_feed_step_done: step %lld is not the last upload (%lld)",
+                 (long long)step, (long long)(t->feed_k - 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host_loss) CUDA_TRY(cudaMemcpyAsync(host_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(t->ev_step_done[step & 1], st));
+    return DSSM_OK;
+}
+
+// upload + single-GPU train step + loss read-back, all asynchronous; returns the step id (< 0 on error)
+extern "C" int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                                    const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream) {
+    const int64_t k = dssm_tower_feed_upload_async(t, host_indptr, host_indices, host_values, nnz, stream);
+    if (k < 0) return k;
+    if (dssm_tower_train_step_staged(t, stream) != DSSM_OK) return -1;
+    if (dssm_tower_feed_step_done(t, k, host_loss, stream) != DSSM_OK) return -1;
     return k;
 }
 

@@ -191,3 +191,14 @@ class DataParallelTower:
         else:
             self._step_staged()
         return t.tensor("loss")
+
+    # ---- pipelined host feed (tower.train_step_host_async for the data-parallel step) ------------------------------
+    def train_step_host_async(self, pinned) -> int:
+        """Upload this rank's CSR from pinned host memory on the tower's copy stream (overlapping the previous step), run
+        the data-parallel step on it, copy the loss back; returns the step id for tower.feed_loss / feed_wait."""
+        t = self.tower
+        k = t.feed_upload_async(pinned)
+        self.train_step(None)
+        t.feed_step_done(k)
+        return k
+

@@ -337,6 +337,20 @@ class DSSMTower:
         self._feed_next = k + 1
         return int(k)
 
+    def feed_upload_async(self, pinned) -> int:
+        """First half of train_step_host_async for callers that run their own step on the staging CSR (DataParallelTower)."""
+        indptr, indices, values, nnz = pinned
+        if getattr(self, "_loss_slots", None) is None:
+            self._loss_slots = torch.zeros(2, dtype=torch.float32).pin_memory()
+        k = lib.dssm_tower_feed_upload_async(self._h, ptr(indptr), ptr(indices), ptr(values), nnz, stream_ptr())
+        if k < 0:
+            raise DssmError(int(k), last_error())
+        return int(k)
+
+    def feed_step_done(self, step: int) -> None:
+        slot = C.c_void_p(self._loss_slots.data_ptr() + 4 * (step & 1))
+        check(lib.dssm_tower_feed_step_done(self._h, step, slot, stream_ptr()))
+
     def feed_wait(self, step: int) -> None:
         check(lib.dssm_tower_feed_wait(self._h, step))
 

@@ -338,6 +338,12 @@ int dssm_tower_train_step_staged(dssm_tower* t, dssm_stream_t stream);
 int64_t dssm_tower_train_step_host_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
                                          const float* host_values, int64_t nnz, float* host_loss, dssm_stream_t stream);
 int dssm_tower_feed_wait(dssm_tower* t, int64_t step);
+/* The two halves of dssm_tower_train_step_host_async for callers that run their own step on the staging CSR (the
+ * data-parallel pipeline): upload (returns the step id k), then -- after enqueuing the step on `stream` --
+ * dssm_tower_feed_step_done(k) copies the loss back and records the completion event dssm_tower_feed_wait(k) waits on. */
+int64_t dssm_tower_feed_upload_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
+                                     const float* host_values, int64_t nnz, dssm_stream_t stream);
+int dssm_tower_feed_step_done(dssm_tower* t, int64_t step, float* host_loss, dssm_stream_t stream);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dssm_tower_launch_count(const dssm_tower* t);
 /* One un-graphed train step on the staging CSR with CUDA events between the phases; synchronises.
