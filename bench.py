@@ -369,7 +369,8 @@ def run_ours(args):
                 "config": describe(conf, args.workload, world, {"mean_nnz_per_step_per_gpu": mean_nnz, "gemm_mode": conf.gemm_mode,
                                                                "distinct_batches": NB, "cuda_graph": True,
                                                                "dp_w1_chunks": (dp.n_chunks if dp else None),
-                                                               "dp_comm": (args.dp_comm if dp else None)}),
+                                                               "dp_comm": (dp.comm if dp else None),
+                                                               "dp_nvls_multicast": (getattr(dp, "use_multicast", None) if dp else None)}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms, "last_loss": last_loss},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "retrieval": retrieval}

@@ -73,6 +73,7 @@ SIGNATURES = {
     "dssm_spmm_bwd_dw_adam": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _i32, _p, _sz, _p]),
     "dssm_spmm_bwd_adam_absent": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _p, _sz, _p]),
     "dssm_w1_shard_reduce_adam": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _f, _f, _f, _p]),
+    "dssm_w1_shard_reduce_adam_mc": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _f, _f, _f, _p]),
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),

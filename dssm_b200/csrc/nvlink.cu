@@ -17,11 +17,11 @@ struct PeerPtrs {
     float4* W[DSSM_MAX_PEERS];
 };
 
-// NR = compile-time bound on the rank count (2, 4, 8, 16).  HOIST: all NCH * n_ranks peer loads of a row are issued before
-// the first use -- a peer load costs an NVLink round trip (~2 us), so bytes in flight per SM, not occupancy, decide
-// whether the pull runs at link rate (at n = 2 a lane has only NCH remote loads to overlap).  For NR = 16 the row is
-// processed one float4 chunk at a time to stay inside the register file.
-template <int NCH, int NR, bool HOIST>
+// NR = compile-time bound on the rank count (2, 4, 8, 16); ROWS = rows a warp handles per iteration.  All
+// ROWS * NCH * n_ranks peer loads of an iteration are issued before the first use: a peer load costs an NVLink round
+// trip (~2-3 us), so the bytes in flight per SM -- not occupancy -- decide whether the pull runs at link rate
+// (measured at n = 2 with one row per iteration: 120 us for 30 MB in + 30 MB out).  ROWS * NR is kept at 8.
+template <int NCH, int NR, int ROWS>
 __global__ void __launch_bounds__(NV_THREADS)
 w1_shard_reduce_adam_kernel(PeerPtrs p, int n_ranks, int self, int L4, int row_begin, int row_end, float4* __restrict__ m,
                             float4* __restrict__ v, const float* __restrict__ beta_pow, float lr, float b1, float b2, float eps) {
@@ -30,87 +30,140 @@ w1_shard_reduce_adam_kernel(PeerPtrs p, int n_ranks, int self, int L4, int row_b
     const float inv_n = 1.0f / (float)n_ranks;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto adam4 = [&](float4 g, float4& pp, float4& mm, float4& vv) {
-#define ADAM1(x)                                          \
-    {                                                     \
-        const float gr = g.x * inv_n;                     \
-        mm.x = b1 * mm.x + (1.f - b1) * gr;               \
-        vv.x = b2 * vv.x + (1.f - b2) * (gr * gr);        \
-        pp.x = pp.x - lr_t * mm.x / (sqrtf(vv.x) + eps);  \
-    }
-        ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
-#undef ADAM1
-    };
-    for (int row = row_begin + blockIdx.x * wpb + (threadIdx.x >> 5); row < row_end; row += gridDim.x * wpb) {
-        if (HOIST) {
-            float4 part[NCH][NR], pp[NCH], mm[NCH], vv[NCH];
+    const int warp_global = blockIdx.x * wpb + (threadIdx.x >> 5), n_warps = gridDim.x * wpb;
+    for (int row0 = row_begin + warp_global * ROWS; row0 < row_end; row0 += n_warps * ROWS) {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int col = lane + 32 * k;
-                const size_t i = (size_t)row * L4 + col;
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            if (col >= L4) continue;
+            float4 part[ROWS][NR], pp[ROWS], mm[ROWS], vv[ROWS];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) part[k][r] = (col < L4 && r < n_ranks) ? __ldcv(p.dW[r] + i) : z4;
+            for (int j = 0; j < ROWS; ++j) {
+                const bool okr = row0 + j < row_end;
+                const size_t i = (size_t)(okr ? row0 + j : row0) * L4 + col;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) part[j][r] = (okr && r < n_ranks) ? __ldcv(p.dW[r] + i) : z4;  // never a stale line
             }
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int col = lane + 32 * k;
-                const size_t i = (size_t)row * L4 + col;
-                if (col < L4) { pp[k] = p.W[self][i]; mm[k] = m[i]; vv[k] = v[i]; }
+            for (int j = 0; j < ROWS; ++j) {
+                const size_t i = (size_t)(row0 + j < row_end ? row0 + j : row0) * L4 + col;
+                pp[j] = p.W[self][i];
+                mm[j] = m[i];
+                vv[j] = v[i];
             }
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int col = lane + 32 * k;
-                if (col >= L4) continue;
-                const size_t i = (size_t)row * L4 + col;
+            for (int j = 0; j < ROWS; ++j) {
+                if (row0 + j >= row_end) continue;
+                const size_t i = (size_t)(row0 + j) * L4 + col;
                 float4 g = z4;
 #pragma unroll
                 for (int r = 0; r < NR; ++r)  // rank order: the one owner of a row fixes the summation order for everybody
-                    if (r < n_ranks) { g.x += part[k][r].x; g.y += part[k][r].y; g.z += part[k][r].z; g.w += part[k][r].w; }
-                adam4(g, pp[k], mm[k], vv[k]);
-                m[i] = mm[k];
-                v[i] = vv[k];
+                    if (r < n_ranks) { g.x += part[j][r].x; g.y += part[j][r].y; g.z += part[j][r].z; g.w += part[j][r].w; }
+#define ADAM1(x)                                                   \
+    {                                                              \
+        const float gr = g.x * inv_n;                              \
+        mm[j].x = b1 * mm[j].x + (1.f - b1) * gr;                  \
+        vv[j].x = b2 * vv[j].x + (1.f - b2) * (gr * gr);           \
+        pp[j].x = pp[j].x - lr_t * mm[j].x / (sqrtf(vv[j].x) + eps); \
+    }
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                m[i] = mm[j];
+                v[i] = vv[j];
 #pragma unroll
                 for (int r = 0; r < NR; ++r)
-                    if (r < n_ranks) p.W[r][i] = pp[k];
+                    if (r < n_ranks) p.W[r][i] = pp[j];
             }
-        } else {
+        }
+    }
+}
+
+// NVLS variant: the buffers are also mapped through an NVSwitch MULTICAST address.  multimem.ld_reduce makes the switch
+// fetch the row from every replica and return the fp32 sum (one response instead of n), multimem.st makes it replicate
+// the new weight row into every replica (one store instead of n): per GPU and direction the wire carries
+// (n-1)/n * |W1| + |W1|/n instead of 2 (n-1)/n * |W1|.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(mc)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int NCH, int ROWS>
+__global__ void __launch_bounds__(NV_THREADS)
+w1_shard_reduce_adam_mc_kernel(const float4* __restrict__ mc_dW, float4* __restrict__ mc_W, const float4* __restrict__ W_local, float inv_n,
+                               int L4, int row_begin, int row_end, float4* __restrict__ m, float4* __restrict__ v,
+                               const float* __restrict__ beta_pow, float lr, float b1, float b2, float eps) {
+    const float b1p = __ldg(beta_pow), b2p = __ldg(beta_pow + 1);
+    const float lr_t = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int warp_global = blockIdx.x * wpb + (threadIdx.x >> 5), n_warps = gridDim.x * wpb;
+    for (int row0 = row_begin + warp_global * ROWS; row0 < row_end; row0 += n_warps * ROWS) {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int col = lane + 32 * k;
-                if (col >= L4) continue;
-                const size_t i = (size_t)row * L4 + col;
-                float4 part[NR];
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            if (col >= L4) continue;
+            float4 g[ROWS], pp[ROWS], mm[ROWS], vv[ROWS];
 #pragma unroll
-                for (int r = 0; r < NR; ++r)
-                    if (r < n_ranks) part[r] = __ldcv(p.dW[r] + i);  // peer memory: never from a stale cache line
-                float4 pp = p.W[self][i], mm = m[i], vv = v[i];
-                float4 g = z4;
+            for (int j = 0; j < ROWS; ++j) {
+                const size_t i = (size_t)(row0 + j < row_end ? row0 + j : row0) * L4 + col;
+                g[j] = multimem_ld_reduce_add(mc_dW + i);
+            }
 #pragma unroll
-                for (int r = 0; r < NR; ++r)
-                    if (r < n_ranks) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-                adam4(g, pp, mm, vv);
-                m[i] = mm;
-                v[i] = vv;
+            for (int j = 0; j < ROWS; ++j) {
+                const size_t i = (size_t)(row0 + j < row_end ? row0 + j : row0) * L4 + col;
+                pp[j] = W_local[i];
+                mm[j] = m[i];
+                vv[j] = v[i];
+            }
 #pragma unroll
-                for (int r = 0; r < NR; ++r)
-                    if (r < n_ranks) p.W[r][i] = pp;
+            for (int j = 0; j < ROWS; ++j) {
+                if (row0 + j >= row_end) continue;
+                const size_t i = (size_t)(row0 + j) * L4 + col;
+#define ADAM1(x)                                                   \
+    {                                                              \
+        const float gr = g[j].x * inv_n;                           \
+        mm[j].x = b1 * mm[j].x + (1.f - b1) * gr;                  \
+        vv[j].x = b2 * vv[j].x + (1.f - b2) * (gr * gr);           \
+        pp[j].x = pp[j].x - lr_t * mm[j].x / (sqrtf(vv[j].x) + eps); \
+    }
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                m[i] = mm[j];
+                v[i] = vv[j];
+                multimem_st(mc_W + i, pp[j]);
             }
         }
     }
 }
 
 template <int NCH>
+static void launch_shard_mc(const float* mc_dW, float* mc_W, const float* W_local, int n_ranks, int L1, int row_begin, int row_end, float* m,
+                            float* v, const float* beta_pow, float lr, float b1, float b2, float eps, cudaStream_t st) {
+    int blocks = sm_count() * 4;
+    const int need = cdiv(row_end - row_begin, NV_THREADS / 32);
+    if (blocks > need) blocks = need;
+    w1_shard_reduce_adam_mc_kernel<NCH, 4><<<blocks, NV_THREADS, 0, st>>>((const float4*)mc_dW, (float4*)mc_W, (const float4*)W_local,
+                                                                          1.0f / (float)n_ranks, L1 / 4, row_begin, row_end, (float4*)m,
+                                                                          (float4*)v, beta_pow, lr, b1, b2, eps);
+}
+
+template <int NCH>
 static void launch_shard(const PeerPtrs& p, int n_ranks, int self, int L1, int row_begin, int row_end, float* m, float* v,
                          const float* beta_pow, float lr, float b1, float b2, float eps, cudaStream_t st) {
-    int blocks = sm_count() * 2;
+    int blocks = sm_count() * 4;
     const int need = cdiv(row_end - row_begin, NV_THREADS / 32);
     if (blocks > need) blocks = need;
 #define NV_ARGS p, n_ranks, self, L1 / 4, row_begin, row_end, (float4*)m, (float4*)v, beta_pow, lr, b1, b2, eps
-    if (n_ranks <= 2) w1_shard_reduce_adam_kernel<NCH, 2, true><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
-    else if (n_ranks <= 4) w1_shard_reduce_adam_kernel<NCH, 4, true><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
-    else if (n_ranks <= 8 && NCH <= 4) w1_shard_reduce_adam_kernel<NCH, 8, true><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
-    else if (n_ranks <= 8) w1_shard_reduce_adam_kernel<NCH, 8, false><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
-    else w1_shard_reduce_adam_kernel<NCH, DSSM_MAX_PEERS, false><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
+    if (n_ranks <= 2) w1_shard_reduce_adam_kernel<NCH, 2, 4><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
+    else if (n_ranks <= 4) w1_shard_reduce_adam_kernel<NCH, 4, 2><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
+    else if (n_ranks <= 8) w1_shard_reduce_adam_kernel<NCH, 8, 1><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
+    else w1_shard_reduce_adam_kernel<NCH, DSSM_MAX_PEERS, 1><<<blocks, NV_THREADS, 0, st>>>(NV_ARGS);
 #undef NV_ARGS
 }
 
@@ -140,3 +193,21 @@ extern "C" int dssm_w1_shard_reduce_adam(const float* const* peer_dW1, float* co
     LAUNCH_CHECK("w1_shard_reduce_adam");
     return DSSM_OK;
 }
+
+extern "C" int dssm_w1_shard_reduce_adam_mc(const float* mc_dW1, float* mc_W1, const float* W1_local, int32_t n_ranks, int32_t D,
+                                            int32_t L1, int32_t row_begin, int32_t row_end, float* m1, float* v1,
+                                            const float* beta_pow, float lr, float beta1, float beta2, float eps, dssm_stream_t stream) {
+    DSSM_REQUIRE(mc_dW1 && mc_W1 && W1_local && m1 && v1 && beta_pow, DSSM_ERR_BAD_ARG, "dssm_w1_shard_reduce_adam_mc: null pointer");
+    DSSM_REQUIRE(n_ranks >= 1, DSSM_ERR_BAD_ARG, "dssm_w1_shard_reduce_adam_mc: n_ranks=%d", n_ranks);
+    DSSM_REQUIRE(D > 0 && L1 > 0 && L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_w1_shard_reduce_adam_mc: bad shape");
+    DSSM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= D, DSSM_ERR_BAD_ARG, "dssm_w1_shard_reduce_adam_mc: bad row range");
+    DSSM_REQUIRE(aligned16(mc_dW1) && aligned16(mc_W1) && aligned16(W1_local) && aligned16(m1) && aligned16(v1), DSSM_ERR_BAD_ALIGN,
+                 "dssm_w1_shard_reduce_adam_mc: buffers must be 16-byte aligned");
+    if (row_begin == row_end) return DSSM_OK;
+    const int nch = cdiv(L1 / 4, 32);
+    DISPATCH_NCH(nch, launch_shard_mc<N_>(mc_dW1, mc_W1, W1_local, n_ranks, L1, row_begin, row_end, m1, v1, beta_pow, lr, beta1, beta2, eps,
+                                          (cudaStream_t)stream));
+    LAUNCH_CHECK("w1_shard_reduce_adam_mc");
+    return DSSM_OK;
+}
+

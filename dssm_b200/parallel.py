@@ -50,12 +50,13 @@ class DataParallelTower:
     capture_graph() records the whole step -- kernels and collectives -- into one CUDA graph, so the ~60 launches
     cost no CPU time per step."""
 
-    def __init__(self, tower, group=None, n_chunks: int = 2, comm: str = "nccl"):
+    def __init__(self, tower, group=None, n_chunks: int = 2, comm: str = "nccl", multicast: Optional[bool] = None):
         if comm not in ("nccl", "nvlink"):
             raise ValueError("comm must be 'nccl' or 'nvlink'")
         self.tower = tower
         self.group = group
         self.comm = comm
+        self.multicast = multicast  # None: use NVSwitch multicast (NVLS) when the symmetric-memory handle offers it
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_chunks = max(1, min(int(n_chunks), 64))
         off, rows, cols = tower._layout[0]["W1"]
@@ -98,6 +99,19 @@ class DataParallelTower:
         arr = C.c_void_p * self.world
         self._peer_w = arr(*[int(p) + 4 * w1_off for p in self._h_params.buffer_ptrs])
         self._peer_dw = arr(*[int(p) + 4 * w1_off for p in self._h_comm.buffer_ptrs])  # grads = comm[:P]
+        has_mc = bool(getattr(self._h_params, "has_multicast_support", False)) and bool(self._h_params.multicast_ptr) \
+            and bool(self._h_comm.multicast_ptr)
+        import os
+
+        # measured (C2, profiles/r1_bench_c2_n{2,8}_*): at n = 2 the multicast path moves the same bytes as plain peer
+        # loads/stores and its multimem instructions are ~15 % slower (0.557 vs 0.484 ms per step); at n = 8 it moves
+        # 59 instead of 104 MB per direction and wins (0.543 vs 0.591 ms).  Default: NVLS from 4 ranks up.
+        env = os.environ.get("DSSM_NVLINK_MULTICAST")
+        want = self.multicast if self.multicast is not None else (env != "0" and (env == "1" or self.world >= 4))
+        self.use_multicast = bool(want) and has_mc
+        if self.use_multicast:
+            self._mc_w = int(self._h_params.multicast_ptr) + 4 * w1_off
+            self._mc_dw = int(self._h_comm.multicast_ptr) + 4 * w1_off
         D = t.conf.TRIGRAM_D
         per = (D + self.world - 1) // self.world
         self.row_begin, self.row_end = min(self.rank * per, D), min((self.rank + 1) * per, D)
@@ -111,9 +125,14 @@ class DataParallelTower:
         w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         t.backward_w1(0, 1)  # this rank's dense dW1, in symmetric memory
         self._h_comm.barrier(channel=0)  # every rank's dW1 is complete and visible
-        check(lib.dssm_w1_shard_reduce_adam(self._peer_dw, self._peer_w, self.world, self.rank, c.TRIGRAM_D, c.layers[0],
-                                            self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate,
-                                            c.beta1, c.beta2, c.adam_eps, stream_ptr()))
+        if self.use_multicast:  # NVLS: in-switch reduction of the gradient rows, in-switch replication of the weight rows
+            check(lib.dssm_w1_shard_reduce_adam_mc(self._mc_dw, self._mc_w, ptr(t.params), self.world, c.TRIGRAM_D, c.layers[0],
+                                                   self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow),
+                                                   c.learning_rate, c.beta1, c.beta2, c.adam_eps, stream_ptr()))
+        else:
+            check(lib.dssm_w1_shard_reduce_adam(self._peer_dw, self._peer_w, self.world, self.rank, c.TRIGRAM_D, c.layers[0],
+                                                self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate,
+                                                c.beta1, c.beta2, c.adam_eps, stream_ptr()))
         w_rest.wait()
         t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
         t.adam_advance()

@@ -138,6 +138,13 @@ int dssm_spmm_bwd_adam_absent(int32_t D, int32_t L1, float* W1, float* m1, float
 int dssm_w1_shard_reduce_adam(const float* const* peer_dW1, float* const* peer_W1, int32_t n_ranks, int32_t self, int32_t D,
                               int32_t L1, int32_t row_begin, int32_t row_end, float* m1, float* v1, const float* beta_pow,
                               float lr, float beta1, float beta2, float eps, dssm_stream_t stream);
+/* The same exchange through an NVSwitch multicast mapping of the two buffers (NVLS): mc_dW1 / mc_W1 are the MULTICAST
+ * addresses of dW1 / W1 (e.g. torch symmetric memory's multicast_ptr), W1_local this rank's ordinary pointer to its own
+ * W1.  multimem.ld_reduce returns the switch-side fp32 sum of a gradient row over all replicas, multimem.st replicates
+ * the new weight row into all of them: per GPU and direction the wire carries |W1| instead of 2(n-1)/n |W1|. */
+int dssm_w1_shard_reduce_adam_mc(const float* mc_dW1, float* mc_W1, const float* W1_local, int32_t n_ranks, int32_t D, int32_t L1,
+                                 int32_t row_begin, int32_t row_end, float* m1, float* v1, const float* beta_pow, float lr,
+                                 float beta1, float beta2, float eps, dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
