@@ -1,0 +1,74 @@
+"""Host batch pipeline (dssm_b200/loader.py): the direct three-memcpy assembly equals pull_batch + stacking
+(utils/utils.py:45-61), the epoch length follows new_dssm.py:46, and the ring never overwrites a buffer that may still be
+in flight."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from dssm_b200 import Config, pull_batch, stack_feed
+from dssm_b200.loader import HostBatchLoader, fill_stacked, reference_epoch_steps
+
+
+def _epoch(n_q, D, NEG, seed=0, dtype=np.int64):
+    rng = np.random.default_rng(seed)
+    mk = lambda n: sp.random(n, D, density=0.03, format="csr", random_state=rng, data_rvs=lambda k: rng.integers(1, 4, k)).astype(dtype)
+    return mk(n_q), mk(n_q), mk(n_q * NEG)
+
+
+def test_epoch_steps_follow_the_reference():
+    assert reference_epoch_steps(1000, 100) == 9  # int(n / BS) - 1
+    assert reference_epoch_steps(150, 100) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float64])
+def test_loader_equals_pull_batch(dtype):
+    B, NEG, D = 8, 3, 200
+    q, p, n = _epoch(50, D, NEG, dtype=dtype)
+    p[3] = 0  # an empty row
+    p.eliminate_zeros()
+    conf = Config(TRIGRAM_D=D, query_BS=B, NEG=NEG, layers=(16, 8))
+    ld = HostBatchLoader(q, p, n, B, NEG, pin=False)
+    assert len(ld) == int(50 / B) - 1
+    got = [(ip.numpy().copy(), ix.numpy()[:nnz].copy(), vl.numpy()[:nnz].copy(), nnz) for ip, ix, vl, nnz in ld]
+    assert len(got) == len(ld)
+    for b, (ip, ix, vl, nnz) in enumerate(got):
+        ref = stack_feed(pull_batch(True, q, p, n, b, B, conf=conf), conf)
+        assert nnz == ref.nnz and ip.dtype == np.int32 and vl.dtype == np.float32
+        assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices) and np.array_equal(vl, ref.values)
+    assert ld.max_nnz == max(g[3] for g in got)
+
+
+def test_loader_shuffled_ids_and_bounds():
+    B, NEG, D = 4, 2, 64
+    q, p, n = _epoch(30, D, NEG, seed=1)
+    conf = Config(TRIGRAM_D=D, query_BS=B, NEG=NEG, layers=(8, 4))
+    ld = HostBatchLoader(q, p, n, B, NEG, pin=False, depth=4)
+    order = [5, 0, 3, 3, 1]
+    for b, (ip, ix, vl, nnz) in zip(order, ld.iterate(order)):
+        ref = stack_feed(pull_batch(True, q, p, n, b, B, conf=conf), conf)
+        assert np.array_equal(ix.numpy()[:nnz], ref.indices)
+    with pytest.raises(IndexError):
+        next(iter(ld.iterate([99])))
+    with pytest.raises(ValueError):
+        HostBatchLoader(q, p, n[:-1], B, NEG, pin=False)
+
+
+def test_ring_does_not_overwrite_batches_in_flight():
+    """A consumer that looks at a batch again while holding the next two (two steps in flight + the one being issued) must
+    still see it intact."""
+    B, NEG, D = 4, 2, 64
+    q, p, n = _epoch(80, D, NEG, seed=2)
+    ld = HostBatchLoader(q, p, n, B, NEG, pin=False, depth=4)
+    held = []
+    for i, item in enumerate(ld):
+        held.append((item, item[1].numpy()[:item[3]].copy()))
+        for (ip, ix, vl, nnz), snap in held[-3:]:
+            assert np.array_equal(ix.numpy()[:nnz], snap)
+    assert len(held) == len(ld)
+
+
+def test_fill_rejects_oversized_batch():
+    q, p, n = _epoch(10, 50, 1, seed=3)
+    ip, ix, vl = np.zeros(31, np.int32), np.zeros(2, np.int32), np.zeros(2, np.float32)
+    with pytest.raises(ValueError):
+        fill_stacked(((q, 0, 10), (p, 0, 10), (n, 0, 10)), ip, ix, vl)
