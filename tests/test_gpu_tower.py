@@ -235,6 +235,32 @@ def test_pipelined_host_feed_matches_synchronous_host_steps():
         b_.train_step_host_async((ip, ix, vl, nnz - 1))  # indptr[R] != nnz
 
 
+def test_host_batch_loader_drives_the_pipelined_feed():
+    """An epoch through HostBatchLoader + train_epoch_host (worker-thread batch assembly, pinned ring, double-buffered
+    upload) trains like the reference-shaped loop over pull_batch feeds (new_dssm.py:261-269)."""
+    import scipy.sparse as sp
+
+    from dssm_b200 import Config, DSSMTower, HostBatchLoader, pull_batch, stack_feed
+    from dssm_b200.synthetic import init_params, sparse_rows
+
+    conf = Config(TRIGRAM_D=2000, query_BS=32, NEG=3, layers=(64, 32))
+    rng = np.random.default_rng(5)
+    nq = 32 * 7
+    mk = lambda n, lam: sp.csr_matrix(sparse_rows(rng, n, conf.TRIGRAM_D, lam), shape=(n, conf.TRIGRAM_D))
+    q, p, n = mk(nq, 8), mk(nq, 16), mk(nq * conf.NEG, 16)
+    loader = HostBatchLoader(q, p, n, conf.query_BS, conf.NEG)
+    assert len(loader) == 6
+    params = init_params(conf, 0)
+    a, b_ = DSSMTower(conf, max_nnz=loader.max_nnz, params=params), DSSMTower(conf, max_nnz=loader.max_nnz, params=params)
+    b_.capture_graph()
+    ref = [a.train_step(a.to_device(stack_feed(pull_batch(True, q, p, n, i, conf.query_BS, conf=conf), conf))).item()
+           for i in range(len(loader))]
+    got = b_.train_epoch_host(loader)
+    assert len(got) == len(ref)
+    for i, (x, y) in enumerate(zip(ref, got)):
+        assert abs(x - y) <= 2e-4 * abs(x), f"step {i}: {x} vs {y}"
+
+
 def test_wrong_batch_shape_is_rejected():
     from dssm_b200 import Config, DSSMTower
     from dssm_b200.synthetic import make_batch
