@@ -162,7 +162,7 @@ class DSSMOracle:
         for l in range(1, self.n_layers + 1):
             W, b = self.p[f"W{l}"], self.p[f"b{l}"]
             if l == 1:
-                h = np.asarray(X.astype(dt) @ W, dtype=dt) + b  # sparse_tensor_dense_matmul :124-126
+                h = self._spmm(X.astype(dt), W) + b  # sparse_tensor_dense_matmul :124-126
             else:
                 h = a @ W + b  # tf.matmul :146-148
             cache[f"h{l}"] = h
@@ -260,7 +260,7 @@ class DSSMOracle:
                 dA = (dh @ self.p[f"W{l}"].T).astype(dt)
             else:
                 X = cache["X"].astype(dt)
-                grads["W1"] = np.asarray(X.T @ dh, dtype=dt)  # A7: dense [D, L1]
+                grads["W1"] = self._spmm_t(X, dh)  # A7: dense [D, L1]
             cache[f"dh{l}"] = dh
         cache["dY"] = dY
         return grads
@@ -273,11 +273,23 @@ class DSSMOracle:
         lr_t = dt.type(cfg.learning_rate) * np.sqrt(one - self.beta2_power) / (one - self.beta1_power)
         b1, b2, eps = dt.type(cfg.beta1), dt.type(cfg.beta2), dt.type(cfg.adam_eps)
         for k, g in grads.items():
-            self.m[k] = (b1 * self.m[k] + (one - b1) * g).astype(dt)
-            self.v[k] = (b2 * self.v[k] + (one - b2) * (g * g)).astype(dt)
-            self.p[k] = (self.p[k] - lr_t * self.m[k] / (np.sqrt(self.v[k]) + eps)).astype(dt)
+            self._adam_tensor(k, g, lr_t, b1, b2, eps)
         self.beta1_power = dt.type(self.beta1_power * b1)
         self.beta2_power = dt.type(self.beta2_power * b2)
+
+    # The three places where the work is proportional to nnz or to the parameter count.  They are separate methods so that
+    # bench.py's CPU legs can run the SAME arithmetic on all host threads (bench.py:ThreadedPort); tests use these.
+    def _spmm(self, X: sp.csr_matrix, W: np.ndarray) -> np.ndarray:
+        return np.asarray(X @ W, dtype=self.dtype)
+
+    def _spmm_t(self, X: sp.csr_matrix, dh: np.ndarray) -> np.ndarray:
+        return np.asarray(X.T @ dh, dtype=self.dtype)
+
+    def _adam_tensor(self, k: str, g: np.ndarray, lr_t, b1, b2, eps) -> None:
+        dt, one = self.dtype, self.dtype.type(1)
+        self.m[k] = (b1 * self.m[k] + (one - b1) * g).astype(dt)
+        self.v[k] = (b2 * self.v[k] + (one - b2) * (g * g)).astype(dt)
+        self.p[k] = (self.p[k] - lr_t * self.m[k] / (np.sqrt(self.v[k]) + eps)).astype(dt)
 
     def train_step(self, X: sp.csr_matrix) -> float:
         """sess.run(train_step, feed_dict=pull_batch(True, ...)), new_dssm.py:267-269."""
