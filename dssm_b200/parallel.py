@@ -105,9 +105,10 @@ class DataParallelTower:
 
         # measured (C2, profiles/r1_bench_c2_n{2,8}_*): at n = 2 the multicast path moves the same bytes as plain peer
         # loads/stores and its multimem instructions are ~15 % slower (0.557 vs 0.484 ms per step); at n = 8 it moves
-        # 59 instead of 104 MB per direction and wins (0.543 vs 0.591 ms).  Default: NVLS from 4 ranks up.
+        # 59 instead of 104 MB per direction and wins (0.543 vs 0.591 ms).  Default: NVLS at 8 ranks and up -- the sizes
+        # it was measured at; n = 4 ran with peer loads/stores only (0.532 ms) and stays there until NVLS is measured too.
         env = os.environ.get("DSSM_NVLINK_MULTICAST")
-        want = self.multicast if self.multicast is not None else (env != "0" and (env == "1" or self.world >= 4))
+        want = self.multicast if self.multicast is not None else (env != "0" and (env == "1" or self.world >= 8))
         self.use_multicast = bool(want) and has_mc
         if self.use_multicast:
             self._mc_w = int(self._h_params.multicast_ptr) + 4 * w1_off
