@@ -137,8 +137,7 @@ class DSSMOracle:
         for seg, sl in self._segments(h.shape[0]):
             x = h[sl]
             if on_train:
-                mean = x.mean(axis=0, dtype=dt)  # A1
-                var = np.mean((x - mean) ** 2, axis=0, dtype=dt)
+                mean, var = self._bn_moments(x)  # A1
                 if update_ema:  # A3/A4
                     for nm, val in (("mean", mean), ("var", var)):
                         key = f"bn{l}_{seg}_ema_{nm}"
@@ -247,8 +246,7 @@ class DSSMOracle:
                     mean, rstd = cache[f"bn{l}_{seg}_mean"], cache[f"bn{l}_{seg}_rstd"]
                     gamma = self.p[f"bn{l}_{seg}_gamma"]
                     xhat = (h[sl] - mean) * rstd
-                    dbeta = g[sl].sum(axis=0, dtype=dt)
-                    dgamma = (g[sl] * xhat).sum(axis=0, dtype=dt)
+                    dbeta, dgamma = self._bn_bwd_sums(g[sl], xhat)
                     dh[sl] = (gamma * rstd) * (g[sl] - dbeta / n - xhat * (dgamma / n))
                     grads[f"bn{l}_{seg}_beta"] = dbeta
                     grads[f"bn{l}_{seg}_gamma"] = dgamma
@@ -279,6 +277,18 @@ class DSSMOracle:
 
     # The three places where the work is proportional to nnz or to the parameter count.  They are separate methods so that
     # bench.py's CPU legs can run the SAME arithmetic on all host threads (bench.py:ThreadedPort); tests use these.
+    # The two places where BatchNorm couples the rows of a batch.  Separate methods so that oracle/syncbn.py can turn them
+    # into cross-replica reductions (SyncBN) without restating the rest of the graph.
+    def _bn_moments(self, x: np.ndarray):
+        dt = self.dtype
+        mean = x.mean(axis=0, dtype=dt)
+        var = np.mean((x - mean) ** 2, axis=0, dtype=dt)
+        return mean, var
+
+    def _bn_bwd_sums(self, g: np.ndarray, xhat: np.ndarray):
+        dt = self.dtype
+        return g.sum(axis=0, dtype=dt), (g * xhat).sum(axis=0, dtype=dt)
+
     def _spmm(self, X: sp.csr_matrix, W: np.ndarray) -> np.ndarray:
         return np.asarray(X @ W, dtype=self.dtype)
 
