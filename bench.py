@@ -262,7 +262,15 @@ def run_ours(args):
     max_nnz = max(b.nnz for b in batches)
     mean_nnz = float(np.mean([b.nnz for b in batches]))
     params = init_params(conf, 0)
-    tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params, symmetric=(world > 1 and args.dp_comm == "nvlink"))
+    want_symm = world > 1 and args.dp_comm == "nvlink"
+    try:
+        tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params, symmetric=want_symm)
+    except Exception as e:  # no symmetric-memory allocator on this box / torch build: NCCL exchange instead, loudly
+        if not want_symm:
+            raise
+        print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); falling back to --dp-comm nccl", file=sys.stderr)
+        args.dp_comm = "nccl"
+        tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params)
     dev_batches = [tower.to_device(b) for b in batches]
     pinned = [tower.pin(b) for b in batches]
     dp = DataParallelTower(tower, comm=args.dp_comm) if world > 1 else None
