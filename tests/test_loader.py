@@ -72,3 +72,28 @@ def test_fill_rejects_oversized_batch():
     ip, ix, vl = np.zeros(31, np.int32), np.zeros(2, np.int32), np.zeros(2, np.float32)
     with pytest.raises(ValueError):
         fill_stacked(((q, 0, 10), (p, 0, 10), (n, 0, 10)), ip, ix, vl)
+
+
+def test_fill_stacked_equals_vstack_on_ragged_inputs():
+    """Property: for any row ranges (empty rows, empty ranges, duplicates across parts) the three-run copy equals
+    scipy's vstack of the same slices."""
+    from hypothesis import given, settings, strategies as st
+
+    rng = np.random.default_rng(7)
+    mats = [sp.random(40, 30, density=d, format="csr", random_state=rng, dtype=np.float64) for d in (0.0, 0.05, 0.3)]
+    for m in mats:
+        m.sort_indices()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 2), st.integers(0, 40), st.integers(0, 40)), min_size=1, max_size=4))
+    def check(spec):
+        parts = [(mats[i], min(a, b), max(a, b)) for i, a, b in spec]
+        R = sum(hi - lo for _, lo, hi in parts)
+        nnz_cap = sum(int(m.indptr[hi] - m.indptr[lo]) for m, lo, hi in parts)
+        ip, ix, vl = np.full(R + 1, -1, np.int32), np.zeros(max(nnz_cap, 1), np.int32), np.zeros(max(nnz_cap, 1), np.float32)
+        nnz = fill_stacked(parts, ip, ix, vl)
+        ref = sp.vstack([m[lo:hi] for m, lo, hi in parts], format="csr") if R else sp.csr_matrix((0, 30))
+        assert nnz == ref.nnz and np.array_equal(ip, ref.indptr.astype(np.int32))
+        assert np.array_equal(ix[:nnz], ref.indices) and np.array_equal(vl[:nnz], ref.data.astype(np.float32))
+
+    check()
