@@ -1,6 +1,6 @@
 """dssm_b200 -- B200-native DSSM two-tower hot path behind the reference's model-building surface.
 
-Importing the package loads libdssm_b200.so (building it with nvcc if absent); there is no CPU fallback.
+The first call into the C ABI loads libdssm_b200.so (building it with nvcc if absent); there is no CPU fallback.
 """
 from ._lib import DssmError, LIB_PATH, lib  # noqa: F401
 from .config import Config, baseline_config  # noqa: F401

@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "lib" / "libdssm_b200.so"
 
 DSSM_OK = 0
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2}
-GEMM = {"fp32": 0, "tc_3xtf32": 1}
+GEMM = {"fp32": 0, "tc_3xtf32": 1, "tc_tf32": 2}
 MAX_LAYERS = 8
 
 
@@ -56,8 +56,6 @@ def _load() -> C.CDLL:
     return C.CDLL(str(LIB_PATH))
 
 
-lib = _load()
-
 _p, _i32, _i64, _f, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/dssm_b200.h one to one
@@ -91,6 +89,9 @@ SIGNATURES = {
     "dssm_cos_softmax_loss_fused": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _i32, _i32, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dssm_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
     "dssm_adam_advance": (C.c_int, [_p, _f, _f, _p]),
+    "dssm_auc_update": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _p]),
+    "dssm_auc_result": (C.c_int, [_p, _p, _i32, _p, _p]),
+    "dssm_accuracy": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "dssm_corpus_topk_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "dssm_corpus_topk": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "dssm_corpus_topk_tc_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
@@ -104,6 +105,8 @@ SIGNATURES = {
     "dssm_tower_num_tensors": (_i32, [_p, _i32]),
     "dssm_tower_tensor_info": (C.c_int, [_p, _i32, _i32, C.c_char_p, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "dssm_tower_bind": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64]),
+    "dssm_tower_syncbn_bytes": (_sz, [_p, _i32]),
+    "dssm_tower_set_syncbn": (C.c_int, [_p, _i32, _i32, _p]),
     "dssm_tower_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p]),
     "dssm_tower_backward": (C.c_int, [_p, _p]),
     "dssm_tower_adam": (C.c_int, [_p, _f, _p]),
@@ -129,10 +132,36 @@ SIGNATURES = {
     "dssm_tower_profile_timeline": (C.c_int, [_p, C.c_char_p, _i32, C.POINTER(C.c_float), _i32, C.POINTER(_i32), _p]),
 }
 
-for _name, (_res, _args) in SIGNATURES.items():
-    _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync
-    _fn.restype = _res
-    _fn.argtypes = _args
+class _LazyLib:
+    """libdssm_b200.so, mapped on the first attribute access (not at import): modules that only need the host-side
+    helpers (config, synthetic batches -- e.g. bench.py's --impl reference arm) never load the product library.  The
+    first access loads it, binds every SIGNATURES entry (AttributeError = header and library out of sync) and then
+    serves attributes straight from the CDLL.  There is still no CPU fallback: a missing library raises here."""
+
+    _cdll = None
+
+    def _bind(self) -> C.CDLL:
+        if _LazyLib._cdll is None:
+            cdll = _load()
+            for _name, (_res, _args) in SIGNATURES.items():
+                _fn = getattr(cdll, _name)
+                _fn.restype = _res
+                _fn.argtypes = _args
+            _LazyLib._cdll = cdll
+        return _LazyLib._cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._bind(), name)
+        self.__dict__[name] = fn
+        return fn
+
+
+lib = _LazyLib()
+
+
+def loaded() -> bool:
+    """True once the shared library has been mapped into this process."""
+    return _LazyLib._cdll is not None
 
 
 def last_error() -> str:

@@ -201,7 +201,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
                      const float* __restrict__ shift, float* __restrict__ part, int n_chunks_total, int chunk_rows,
                      int* __restrict__ tickets, const float* __restrict__ gamma, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ db /* [L] or NULL */) {
+                     float* __restrict__ dbeta, float* __restrict__ db /* [L] or NULL */,
+                     float* __restrict__ sumx_out /* [2][L] or NULL: sum of xhat per instance (SyncBN needs it for db) */) {
     __shared__ float red0[BN_TY_BWD][BN_TX + 1];
     __shared__ float red1[BN_TY_BWD][BN_TX + 1];
     __shared__ float red2[BN_TY_BWD][BN_TX + 1];
@@ -292,6 +293,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ H, 
             if (c0 < c1) {
                 dbeta[i] = b;
                 dgamma[i] = g;
+                if (sumx_out) sumx_out[i] = x;
                 const float n = sg_ == 0 ? (float)B : (float)(R - B);
                 dbv = -(__ldg(gamma + i) * __ldg(rstd + i)) * g * (x / n);
             }
@@ -447,6 +449,43 @@ extern "C" int dssm_bn_act_apply(const float* X, int32_t R, int32_t L, int32_t B
     return DSSM_OK;
 }
 
+// The two passes of the backward, separately (SyncBN exchanges [dbeta | dgamma] between them; tower.cu).
+extern "C" int dssm_bn_bwd_reduce_only(const float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act, const float* gamma,
+                                       const float* mean, const float* rstd, const float* scale, const float* shift, float* dgamma,
+                                       float* dbeta, float* db, float* sumx, void* workspace, size_t workspace_bytes,
+                                       dssm_stream_t stream) {
+    DSSM_REQUIRE(dA && H && gamma && mean && rstd && scale && shift && dgamma && dbeta, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null BN pointer");
+    DSSM_REQUIRE(R > 0 && L > 0 && B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
+    const int cr = bn_chunk_rows(R, B);
+    const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
+    DSSM_REQUIRE(workspace && workspace_bytes >= bn_ticket_bytes(L) + (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
+                 "dssm_bn_act_backward: workspace too small");
+    int* tickets = (int*)workspace;
+    float* part = (float*)((char*)workspace + bn_ticket_bytes(L));
+    dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY_BWD);
+    bn_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr, tickets, gamma,
+                                                                    dgamma, dbeta, db, sumx);
+    LAUNCH_CHECK("bn_bwd_reduce");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_bn_bwd_apply_only(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act, const float* gamma,
+                                      const float* mean, const float* rstd, const float* scale, const float* shift, const float* dgamma,
+                                      const float* dbeta, dssm_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (L % 4 == 0 && aligned16(dA) && aligned16(H) && aligned16(gamma) && aligned16(mean) && aligned16(rstd) && aligned16(scale) &&
+        aligned16(shift) && aligned16(dgamma) && aligned16(dbeta)) {
+        dim3 grid(cdiv(R, EW4_ROWS), cdiv(L / 4, 128));
+        bn_bwd_apply_v4_kernel<<<grid, 128, 0, st>>>((float4*)dA, (const float4*)H, R, L / 4, B, act, (const float4*)gamma,
+                                                    (const float4*)mean, (const float4*)rstd, (const float4*)scale,
+                                                    (const float4*)shift, (const float4*)dgamma, (const float4*)dbeta);
+    } else {
+        bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift, dgamma, dbeta);
+    }
+    LAUNCH_CHECK("bn_bwd_apply");
+    return DSSM_OK;
+}
+
 extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act,
                                     const float* gamma, const float* mean, const float* rstd, const float* scale,
                                     const float* shift, float* dgamma, float* dbeta, float* db, void* workspace,
@@ -459,27 +498,8 @@ extern "C" int dssm_bn_act_backward(float* dA, const float* H, int32_t R, int32_
         LAUNCH_CHECK("act_bwd");
         return DSSM_OK;
     }
-    DSSM_REQUIRE(gamma && mean && rstd && shift && dgamma && dbeta, DSSM_ERR_BAD_ARG, "dssm_bn_act_backward: null BN pointer");
-    DSSM_REQUIRE(B > 0 && B <= R, DSSM_ERR_BAD_SHAPE, "dssm_bn_act_backward: need 0 < B <= R");
-    const int cr = bn_chunk_rows(R, B);
-    const int nq = bn_chunks_of(B, cr), nd = bn_chunks_of(R - B, cr), nt = nq + nd;
-    DSSM_REQUIRE(workspace && workspace_bytes >= bn_ticket_bytes(L) + (size_t)3 * nt * L * sizeof(float), DSSM_ERR_WORKSPACE,
-                 "dssm_bn_act_backward: workspace too small");
-    int* tickets = (int*)workspace;
-    float* part = (float*)((char*)workspace + bn_ticket_bytes(L));
-    dim3 grid(cdiv(L, BN_TX), nt), block(BN_TX, BN_TY_BWD);
-    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dA, H, R, L, B, act, mean, rstd, scale, shift, part, nt, cr, tickets, gamma, dgamma,
-                                                  dbeta, db);
-    LAUNCH_CHECK("bn_bwd_reduce");
-    if (L % 4 == 0 && aligned16(dA) && aligned16(H) && aligned16(gamma) && aligned16(mean) && aligned16(rstd) && aligned16(scale) &&
-        aligned16(shift) && aligned16(dgamma) && aligned16(dbeta)) {
-        dim3 grid(cdiv(R, EW4_ROWS), cdiv(L / 4, 128));
-        bn_bwd_apply_v4_kernel<<<grid, 128, 0, st>>>((float4*)dA, (const float4*)H, R, L / 4, B, act, (const float4*)gamma,
-                                                    (const float4*)mean, (const float4*)rstd, (const float4*)scale,
-                                                    (const float4*)shift, (const float4*)dgamma, (const float4*)dbeta);
-    } else {
-        bn_bwd_apply_kernel<<<row_blocks(R), 256, 0, st>>>(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift, dgamma, dbeta);
-    }
-    LAUNCH_CHECK("bn_bwd_apply");
-    return DSSM_OK;
+    int rc = dssm_bn_bwd_reduce_only(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift, dgamma, dbeta, db, nullptr, workspace,
+                                     workspace_bytes, stream);
+    if (rc != DSSM_OK) return rc;
+    return dssm_bn_bwd_apply_only(dA, H, R, L, B, act, gamma, mean, rstd, scale, shift, dgamma, dbeta, stream);
 }

@@ -41,6 +41,19 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int sm_count();
 
+// "do once per device" latch for cudaFuncSetAttribute calls (function attributes are per device, and a process may
+// drive several devices): `static PerDeviceOnce once; if (once.need()) { ...set attributes... }`
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // bump allocator over a caller-provided workspace
 struct Arena {
     char* base;

@@ -206,14 +206,16 @@ using namespace dssm;
 // tcgen05 path (fc_tc.cu)
 extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N);
 extern "C" int dssm_fc_fwd_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t,
-                              const float*, const float*, int32_t, float*, void*, size_t, dssm_stream_t);
-extern "C" int dssm_fc_bwd_dx_tc(const float*, int32_t, int32_t, const float*, int32_t, float*, void*, size_t, dssm_stream_t);
+                              const float*, const float*, int32_t, float*, void*, size_t, int32_t, dssm_stream_t);
+extern "C" int dssm_fc_bwd_dx_tc(const float*, int32_t, int32_t, const float*, int32_t, float*, void*, size_t, int32_t, dssm_stream_t);
 extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_t N);
 extern "C" int dssm_fc_bwd_dw_tc(const float*, int32_t, int32_t, int32_t, const float*, const float*, int32_t, const float*,
-                                 int32_t, float*, int32_t*, dssm_stream_t);
+                                 int32_t, float*, int32_t*, int32_t, dssm_stream_t);
+static inline bool is_tc(int mode) { return mode == DSSM_GEMM_TC_3XTF32 || mode == DSSM_GEMM_TC_TF32; }
+static inline int tc_passes(int mode) { return mode == DSSM_GEMM_TC_TF32 ? 1 : 3; }
 
 extern "C" size_t dssm_fc_fwd_workspace_bytes(int32_t K, int32_t N, int32_t gemm_mode) {
-    return gemm_mode == DSSM_GEMM_TC_3XTF32 ? dssm_fc_tc_workspace_bytes(K, N) : 0;
+    return is_tc(gemm_mode) ? dssm_fc_tc_workspace_bytes(K, N) : 0;
 }
 
 extern "C" int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
@@ -222,8 +224,8 @@ extern "C" int dssm_fc_fwd(const float* Hprev, int32_t R, int32_t K, int32_t B, 
     DSSM_REQUIRE(Hprev && W && Hout, DSSM_ERR_BAD_ARG, "dssm_fc_fwd: null pointer");
     DSSM_REQUIRE((scale == nullptr) == (shift == nullptr), DSSM_ERR_BAD_ARG, "dssm_fc_fwd: scale/shift must both be set or both NULL");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_fwd: bad shape R=%d K=%d N=%d", R, K, N);
-    if (gemm_mode == DSSM_GEMM_TC_3XTF32)
-        return dssm_fc_fwd_tc(Hprev, R, K, B, scale, shift, act, W, bias, N, Hout, workspace, workspace_bytes, stream);
+    if (is_tc(gemm_mode))
+        return dssm_fc_fwd_tc(Hprev, R, K, B, scale, shift, act, W, bias, N, Hout, workspace, workspace_bytes, tc_passes(gemm_mode), stream);
     DSSM_REQUIRE(gemm_mode == DSSM_GEMM_FP32, DSSM_ERR_BAD_ARG, "dssm_fc_fwd: unknown gemm_mode %d", gemm_mode);
     GemmArgs g{Hprev, W, Hout, bias, R, N, K, scale, shift, act, B, 0};
     dim3 grid(cdiv(N, BN), cdiv(R, BM), 1);
@@ -236,7 +238,7 @@ extern "C" int dssm_fc_bwd_dx(const float* dH, int32_t R, int32_t N, const float
                               int32_t gemm_mode, void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
     DSSM_REQUIRE(dH && W && dA, DSSM_ERR_BAD_ARG, "dssm_fc_bwd_dx: null pointer");
     DSSM_REQUIRE(R > 0 && K > 0 && N > 0, DSSM_ERR_BAD_SHAPE, "dssm_fc_bwd_dx: bad shape");
-    if (gemm_mode == DSSM_GEMM_TC_3XTF32) return dssm_fc_bwd_dx_tc(dH, R, N, W, K, dA, workspace, workspace_bytes, stream);
+    if (is_tc(gemm_mode)) return dssm_fc_bwd_dx_tc(dH, R, N, W, K, dA, workspace, workspace_bytes, tc_passes(gemm_mode), stream);
     // C[R,K] = dH[R,N] . W[K,N]^T : reduce over N
     GemmArgs g{dH, W, dA, nullptr, R, K, N, nullptr, nullptr, DSSM_ACT_NONE, 0, 0};
     dim3 grid(cdiv(K, BN), cdiv(R, BM), 1);
@@ -285,8 +287,8 @@ extern "C" int dssm_fc_bwd_dw(const float* Hprev, int32_t R, int32_t K, int32_t 
     int splits = pick_splits(R);
     float* part = (float*)workspace;
     const size_t part_bytes = dssm_fc_bwd_dw_workspace_bytes(R, K, N) - dssm_colsum_workspace_bytes(R, N);
-    if (gemm_mode == DSSM_GEMM_TC_3XTF32) {
-        int rc = dssm_fc_bwd_dw_tc(Hprev, R, K, B, scale, shift, act, dH, N, part, &splits, stream);
+    if (is_tc(gemm_mode)) {
+        int rc = dssm_fc_bwd_dw_tc(Hprev, R, K, B, scale, shift, act, dH, N, part, &splits, tc_passes(gemm_mode), stream);
         if (rc != DSSM_OK) return rc;
     } else {
         const int kps = cdiv(R, splits);

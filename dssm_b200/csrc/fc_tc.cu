@@ -61,6 +61,7 @@ struct Args {
     int M, N, K, ldb, act, Bseg, BN;
     int k_per_split;  // MN mode: rows of the reduction handled by one blockIdx.z (multiple of BK)
     const char* Bimg;  // K-major mode: pre-split, pre-swizzled image of B (make_b_image_kernel); NULL = stage B in registers
+    int passes;        // 3: error-compensated 3xTF32 (1e-5 parity); 1: one tf32 MMA per product (DSSM_GEMM_TC_TF32)
 };
 
 // write one float4 (hi and lo parts) into a swizzled K-major tile: row r, 16-byte chunk c
@@ -241,9 +242,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
                 // 128-byte k lines (MN-major)
                 const uint64_t adv = MN ? (uint64_t)((ks * MN_K8_BYTES) >> 4) : (uint64_t)((ks * 8 * 4) >> 4);
                 const uint32_t acc = tmem_d + (uint32_t)((kb % nacc_used) * MAX_BN);
-                mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= nacc_used || ks > 0) ? 1u : 0u);
-                mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
-                mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                const uint32_t first = (kb >= nacc_used || ks > 0) ? 1u : 0u;
+                if (g.passes == 3) {
+                    mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, first);
+                    mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                    mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                } else {
+                    mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, first);
+                }
             }
             mma_commit(&empty_bar[st]);                // stage reusable when these MMAs have read it
             if (kb == nkb - 1) mma_commit(&done_bar);  // accumulators complete
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
                     hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
                     lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
                     *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
-                    *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
+                    if (g.passes == 3) *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
                 }
                 fence_proxy_async();  // this thread's generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&full_a[st]);
@@ -473,9 +479,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
-                    mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, (kb >= nacc_used || ks > 0) ? 1u : 0u);
-                    mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
-                    mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                    const uint32_t first = (kb >= nacc_used || ks > 0) ? 1u : 0u;
+                    if (g.passes == 3) {
+                        mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, first);
+                        mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                        mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                    } else {
+                        mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, first);
+                    }
                 }
                 mma_commit(&empty_bar[st]);
                 if (kb == nkb - 1) mma_commit(&done_bar);
@@ -568,14 +579,13 @@ static int pick_bn(int N) {
 static size_t smem_bytes(int BN) { return (size_t)STAGES * (2 * A_TILE_BYTES + 2 * (size_t)BN * BK * 4) + 1024; }
 
 static int launch(const Args& a, cudaStream_t st, int splits = 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
-        attr_set = true;
     }
     if (splits > 0) {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM), splits);
@@ -634,19 +644,21 @@ extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int3
     return for_dx ? build_image(W, K, N, N, 0, (char*)img, (cudaStream_t)stream) : build_image(W, N, K, N, 1, (char*)img, (cudaStream_t)stream);
 }
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
-                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, dssm_stream_t stream) {
-    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)img};
+                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes,
+                                  dssm_stream_t stream) {
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)img, passes};
     return tc::launch(a, (cudaStream_t)stream);
 }
-extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, dssm_stream_t stream) {
-    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)img};
+extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes,
+                                     dssm_stream_t stream) {
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)img, passes};
     return tc::launch(a, (cudaStream_t)stream);
 }
 
 // forward on the tensor cores: B = W^T as a pre-split swizzled image in `workspace`
 extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                               int32_t act, const float* W, const float* bias, int32_t N, float* Hout, void* workspace,
-                              size_t workspace_bytes, dssm_stream_t stream) {
+                              size_t workspace_bytes, int32_t passes, dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(Hprev) && aligned16(W) && aligned16(Hout) && (!bias || aligned16(bias)) && (!scale || (aligned16(scale) && aligned16(shift))),
                  DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
@@ -655,13 +667,13 @@ extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = build_image(W, N, K, N, 1, (char*)workspace, st);  // B[n][k] = W[k][n]
     if (rc != DSSM_OK) return rc;
-    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)workspace};
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)workspace, passes};
     return tc::launch(a, st);
 }
 
 // dA[R,K] = dH[R,N] . W[K,N]^T on the tensor cores: B = W (rows = K_layer, reduction = N_layer) as an image
 extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const float* W, int32_t K, float* dA, void* workspace,
-                                 size_t workspace_bytes, dssm_stream_t stream) {
+                                 size_t workspace_bytes, int32_t passes, dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(dH) && aligned16(W) && aligned16(dA), DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
     DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(K, N) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
@@ -670,7 +682,7 @@ extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const fl
     int rc = build_image(W, K, N, N, 0, (char*)workspace, st);  // B[n'=k_layer][k'=n_layer] = W[k_layer][n_layer]
     if (rc != DSSM_OK) return rc;
     // D[M=R, N'=K] = A[M=R, K'=N] . B[N'=K, K'=N]^T
-    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)workspace};
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)workspace, passes};
     return tc::launch(a, st);
 }
 
@@ -683,7 +695,7 @@ extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_
 }
 
 extern "C" int dssm_fc_bwd_dw_tc(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
-                                 int32_t act, const float* dH, int32_t N, float* partials, int32_t* splits_out,
+                                 int32_t act, const float* dH, int32_t N, float* partials, int32_t* splits_out, int32_t passes,
                                  dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(Hprev) && aligned16(dH) && aligned16(partials) && (!scale || (aligned16(scale) && aligned16(shift))),
@@ -694,7 +706,7 @@ extern "C" int dssm_fc_bwd_dw_tc(const float* Hprev, int32_t R, int32_t K, int32
     int kps = cdiv(R, splits);
     kps = (kps + tc::BK - 1) / tc::BK * tc::BK;
     // D[M=K_layer, N] ; reduction over the R rows
-    tc::Args a{Hprev, dH, partials, nullptr, scale, shift, K, N, R, 0, act, B, bn, kps, nullptr};
+    tc::Args a{Hprev, dH, partials, nullptr, scale, shift, K, N, R, 0, act, B, bn, kps, nullptr, passes};
     *splits_out = splits;
     return tc::launch(a, (cudaStream_t)stream, splits);
 }

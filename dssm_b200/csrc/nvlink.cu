@@ -167,6 +167,139 @@ static void launch_shard(const PeerPtrs& p, int n_ranks, int self, int L1, int r
 #undef NV_ARGS
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SyncBN: global-batch BatchNorm moments under data parallelism (new_dssm.py:77 computes tf.nn.moments over the WHOLE
+// batch; n replicas with per-replica moments are a different model).  Every rank owns a small peer-mapped exchange
+// buffer:   [ flags u32[DSSM_MAX_PEERS] | epoch u32 | pad to 512 B | slots[point][rank][4*Lmax] floats ]
+// One single-CTA kernel per BN instance pair and direction: PUSH this rank's [2][L] statistics into slot[point][self] of
+// every rank, cross-GPU barrier (flag[self] = epoch in every rank's buffer with st.release.sys; spin on the own flags
+// with ld.acquire.sys), then merge the n slots locally in rank order -- every rank computes identical bits.
+//   forward   mean = avg_r mean_r ;  var = avg_r (var_r + (mean_r - mean)^2)          (equal row counts: Chan's merge)
+//   backward  dbeta, dgamma = avg_r of the local column sums (each replica's loss is divided by its LOCAL query_BS, so
+//             the average restores the global-batch sums; oracle/syncbn.py states the contract)
+// A slot region is written again only one full step later, and the other exchange points of the step lie in between, so
+// no reader can still be on it.
+constexpr int SYNCBN_HEADER_BYTES = 512;
+constexpr int SYNCBN_THREADS = 512;
+
+struct SyncBnPeers {
+    char* buf[DSSM_MAX_PEERS];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all threads of the (single) CTA call this after their pushes
+__device__ __forceinline__ void syncbn_barrier(const SyncBnPeers& p, int n, int self) {
+    __shared__ uint32_t s_epoch;
+    __threadfence_system();  // this thread's pushes are visible system-wide before the flag goes up
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* ep = reinterpret_cast<uint32_t*>(p.buf[self] + DSSM_MAX_PEERS * sizeof(uint32_t));
+        s_epoch = *ep + 1u;
+        *ep = s_epoch;
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    if ((int)threadIdx.x < n) {
+        st_release_sys(reinterpret_cast<uint32_t*>(p.buf[threadIdx.x]) + self, epoch);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(p.buf[self]) + threadIdx.x;
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float* syncbn_slot(const SyncBnPeers& p, int owner, int point, int n, int rank, int slot_floats) {
+    return reinterpret_cast<float*>(p.buf[owner] + SYNCBN_HEADER_BYTES) + ((size_t)point * n + rank) * slot_floats;
+}
+
+__global__ void __launch_bounds__(SYNCBN_THREADS)
+syncbn_fwd_kernel(SyncBnPeers p, int n, int self, int point, int slot_floats, int L, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ ema_mean, float* __restrict__ ema_var, float* __restrict__ mean,
+                  float* __restrict__ var, float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, float eps,
+                  float decay, int update_ema) {
+    const int L2 = 2 * L;
+    for (int i = threadIdx.x; i < L2; i += blockDim.x) {
+        const float m = mean[i], v = var[i];
+        for (int r = 0; r < n; ++r) {
+            float* dst = syncbn_slot(p, r, point, n, self, slot_floats);
+            dst[i] = m;
+            dst[L2 + i] = v;
+        }
+    }
+    syncbn_barrier(p, n, self);
+    const float inv_n = 1.0f / (float)n;
+    for (int i = threadIdx.x; i < L2; i += blockDim.x) {
+        float mu = 0.f;
+        for (int r = 0; r < n; ++r) mu += __ldcv(syncbn_slot(p, self, point, n, r, slot_floats) + i);
+        mu *= inv_n;
+        float vv = 0.f;
+        for (int r = 0; r < n; ++r) {
+            const float* s = syncbn_slot(p, self, point, n, r, slot_floats);
+            const float d = __ldcv(s + i) - mu;
+            vv += __ldcv(s + L2 + i) + d * d;
+        }
+        vv *= inv_n;
+        if (update_ema) {  // the shadows follow the GLOBAL moments: identical on every replica
+            const float em = ema_mean[i], ev = ema_var[i];
+            ema_mean[i] = em - (1.f - decay) * (em - mu);
+            ema_var[i] = ev - (1.f - decay) * (ev - vv);
+        }
+        const float rs = 1.0f / sqrtf(vv + eps);
+        const float sc = rs * gamma[i];
+        mean[i] = mu;
+        var[i] = vv;
+        rstd[i] = rs;
+        scale[i] = sc;
+        shift[i] = beta[i] - mu * sc;
+    }
+}
+
+__global__ void __launch_bounds__(SYNCBN_THREADS)
+syncbn_bwd_kernel(SyncBnPeers p, int n, int self, int point, int slot_floats, int L, int n_q, int n_d, const float* __restrict__ gamma,
+                  const float* __restrict__ rstd, const float* __restrict__ sumx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                  float* __restrict__ db) {
+    __shared__ float s_db[2 * 1024];
+    const int L2 = 2 * L;
+    for (int i = threadIdx.x; i < L2; i += blockDim.x) {
+        const float b = dbeta[i], g = dgamma[i];
+        for (int r = 0; r < n; ++r) {
+            float* dst = syncbn_slot(p, r, point, n, self, slot_floats);
+            dst[i] = b;
+            dst[L2 + i] = g;
+        }
+    }
+    syncbn_barrier(p, n, self);
+    const float inv_n = 1.0f / (float)n;
+    for (int i = threadIdx.x; i < L2; i += blockDim.x) {
+        float b = 0.f, g = 0.f;
+        for (int r = 0; r < n; ++r) {
+            const float* s = syncbn_slot(p, self, point, n, r, slot_floats);
+            b += __ldcv(s + i);
+            g += __ldcv(s + L2 + i);
+        }
+        b *= inv_n;
+        g *= inv_n;
+        const float b_loc = dbeta[i];
+        const float rows = i < L ? (float)n_q : (float)n_d;
+        // sum over the LOCAL rows of dH = gamma*rstd*(g - dbeta/n - xhat*dgamma/n): the pre-BN bias gradient of this replica
+        if (i < 2 * 1024) s_db[i] = (gamma[i] * rstd[i]) * ((b_loc - b) - (sumx[i] / rows) * g);
+        dbeta[i] = b;
+        dgamma[i] = g;
+    }
+    __syncthreads();
+    if (db)
+        for (int c = threadIdx.x; c < L; c += blockDim.x) db[c] = s_db[c] + s_db[L + c];
+}
+
 }  // namespace dssm
 
 using namespace dssm;
@@ -211,3 +344,45 @@ extern "C" int dssm_w1_shard_reduce_adam_mc(const float* mc_dW1, float* mc_W1, c
     return DSSM_OK;
 }
 
+
+// ---- SyncBN exchange (internal: called by the tower, tower.cu) --------------------------------------------------------
+extern "C" size_t dssm_syncbn_buffer_bytes(int32_t n_ranks, int32_t n_points, int32_t Lmax) {
+    return align_up((size_t)SYNCBN_HEADER_BYTES + (size_t)n_points * n_ranks * 4 * Lmax * sizeof(float), 256);
+}
+
+static int syncbn_peers(void* const* peer_bufs, int n_ranks, int self, SyncBnPeers* out) {
+    DSSM_REQUIRE(peer_bufs && n_ranks >= 1 && n_ranks <= DSSM_MAX_PEERS && self >= 0 && self < n_ranks, DSSM_ERR_BAD_ARG,
+                 "syncbn: n_ranks=%d self=%d (at most %d peers)", n_ranks, self, DSSM_MAX_PEERS);
+    for (int r = 0; r < n_ranks; ++r) {
+        DSSM_REQUIRE(peer_bufs[r] && aligned16(peer_bufs[r]), DSSM_ERR_BAD_ALIGN, "syncbn: peer buffer %d null or unaligned", r);
+        out->buf[r] = (char*)peer_bufs[r];
+    }
+    return DSSM_OK;
+}
+
+extern "C" int dssm_syncbn_forward(void* const* peer_bufs, int32_t n_ranks, int32_t self, int32_t point, int32_t Lmax, int32_t L,
+                                   const float* gamma, const float* beta, float* ema_mean, float* ema_var, float* mean, float* var,
+                                   float* rstd, float* scale, float* shift, float eps, float decay, int32_t update_ema,
+                                   dssm_stream_t stream) {
+    SyncBnPeers p{};
+    int rc = syncbn_peers(peer_bufs, n_ranks, self, &p);
+    if (rc != DSSM_OK) return rc;
+    DSSM_REQUIRE(L > 0 && L <= Lmax, DSSM_ERR_BAD_SHAPE, "syncbn: L=%d exceeds Lmax=%d", L, Lmax);
+    syncbn_fwd_kernel<<<1, SYNCBN_THREADS, 0, (cudaStream_t)stream>>>(p, n_ranks, self, point, 4 * Lmax, L, gamma, beta, ema_mean, ema_var, mean,
+                                                                     var, rstd, scale, shift, eps, decay, update_ema);
+    LAUNCH_CHECK("syncbn_fwd");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_syncbn_backward(void* const* peer_bufs, int32_t n_ranks, int32_t self, int32_t point, int32_t Lmax, int32_t L,
+                                    int32_t n_q, int32_t n_d, const float* gamma, const float* rstd, const float* sumx, float* dgamma,
+                                    float* dbeta, float* db, dssm_stream_t stream) {
+    SyncBnPeers p{};
+    int rc = syncbn_peers(peer_bufs, n_ranks, self, &p);
+    if (rc != DSSM_OK) return rc;
+    DSSM_REQUIRE(L > 0 && L <= Lmax && L <= 1024, DSSM_ERR_BAD_SHAPE, "syncbn: L=%d exceeds min(Lmax=%d, 1024)", L, Lmax);
+    syncbn_bwd_kernel<<<1, SYNCBN_THREADS, 0, (cudaStream_t)stream>>>(p, n_ranks, self, point, 4 * Lmax, L, n_q, n_d, gamma, rstd, sumx, dgamma,
+                                                                     dbeta, db);
+    LAUNCH_CHECK("syncbn_bwd");
+    return DSSM_OK;
+}

@@ -231,12 +231,15 @@ spmm_bwd_scatter_scalar_kernel(const int* __restrict__ indptr, const int* __rest
 //
 //  csc_hist     colcnt[c] += 1 for every non-zero                       (int atomics, exact)
 //  csc_scan_*   colptr = exclusive_scan(colcnt); itemptr = exclusive_scan(max(1, ceil(cnt/CSC_CHUNK)))
-//  csc_fill     (row, value) of every non-zero into its column segment  (slot by atomic cursor)
-//  dw_gather    one warp per item (<= CSC_CHUNK entries of one column): sum value * dH[row,:];
+//  csc_fill     (row, value) of every non-zero into its column segment of a scratch copy (slot by atomic cursor)
+//  csc_sort_*   every column segment is put in ROW order (a row occurs at most once per column, so this is a
+//               counting sort with unique keys: row bitmap in shared memory + popcount prefix = rank), written to
+//               csc_row / csc_val.  Slots handed out by the atomics differ from run to run; the sorted segments do not.
+//  dw_gather    one warp per item (<= CSC_CHUNK entries of one column): sum value * dH[row,:] in entry order;
 //               single-item columns write their dW1 row directly; multi-item columns park partial sums
 //               and the last-arriving item adds them in item order.
-// The slot order inside a column is whatever the atomics gave, so the fp32 summation order of a column
-// can differ between runs (last-bit differences); counts, columns and the set of terms are exact.
+// Every dW1 row is therefore summed in one fixed order (rows ascending, chunk partials in chunk order): the train
+// step is bit-reproducible run to run, like the reference on TF-CPU.
 
 __global__ void csc_hist_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int R,
                                 int* __restrict__ colcnt) {
@@ -350,6 +353,114 @@ csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
             csc_row[slot] = row;
             csc_val[slot] = __ldg(values + p);
         }
+    }
+}
+
+// Row-order every column segment of the scratch CSC (tmp_row / tmp_val, slots as the atomics gave them) into
+// csc_row / csc_val.  Keys are unique inside a column, so rank(row) = number of set bits below `row` in the column's
+// row bitmap.  Small kernel: one warp per column -- <= 32 entries by comparison counting in registers, up to
+// SORT_WARP_MAX entries with a warp-private bitmap in shared memory; longer columns are queued for the block kernel.
+constexpr int SORT_WARP_MAX = 2048;
+constexpr int SORT_BIG_THREADS = 512;
+
+__device__ __forceinline__ void bitmap_rank_scatter(const int* __restrict__ tmp_row, const float* __restrict__ tmp_val, int p,
+                                                    int cnt, const uint32_t* bm, const int* pre, int* __restrict__ csc_row,
+                                                    float* __restrict__ csc_val, int tid, int nthreads) {
+    for (int i = tid; i < cnt; i += nthreads) {
+        const int r = tmp_row[p + i];
+        const float v = tmp_val[p + i];
+        const int rank = pre[r >> 5] + __popc(bm[r >> 5] & ((1u << (r & 31)) - 1u));
+        csc_row[p + rank] = r;
+        csc_val[p + rank] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SPMM_THREADS)
+csc_sort_small_kernel(const int* __restrict__ colcnt, const int* __restrict__ colptr, const int* __restrict__ tmp_row,
+                      const float* __restrict__ tmp_val, int* __restrict__ csc_row, float* __restrict__ csc_val, int D, int words,
+                      int* __restrict__ big_ctl, int* __restrict__ big_list) {
+    extern __shared__ uint32_t sort_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t* bm = sort_smem + (size_t)w * 2 * words;
+    int* pre = reinterpret_cast<int*>(bm + words);
+    for (int c = blockIdx.x * wpb + w; c < D; c += gridDim.x * wpb) {
+        const int cnt = __ldg(colcnt + c);
+        if (cnt == 0) continue;
+        const int p = __ldg(colptr + c);
+        if (cnt <= 32) {
+            int r = 0x7fffffff;
+            float v = 0.f;
+            if (lane < cnt) { r = tmp_row[p + lane]; v = tmp_val[p + lane]; }
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) rank += __shfl_sync(0xffffffffu, r, j) < r ? 1 : 0;
+            if (lane < cnt) { csc_row[p + rank] = r; csc_val[p + rank] = v; }
+        } else if (cnt <= SORT_WARP_MAX) {
+            for (int i = lane; i < words; i += 32) bm[i] = 0u;
+            __syncwarp();
+            for (int i = lane; i < cnt; i += 32) {
+                const int r = tmp_row[p + i];
+                atomicOr(bm + (r >> 5), 1u << (r & 31));
+            }
+            __syncwarp();
+            // exclusive popcount prefix over the bitmap words: lane owns a contiguous run of words
+            const int per = (words + 31) / 32, lo = lane * per, hi = min(words, lo + per);
+            int sum = 0;
+            for (int i = lo; i < hi; ++i) sum += __popc(bm[i]);
+            int x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            int run = x - sum;
+            for (int i = lo; i < hi; ++i) { pre[i] = run; run += __popc(bm[i]); }
+            __syncwarp();
+            bitmap_rank_scatter(tmp_row, tmp_val, p, cnt, bm, pre, csc_row, csc_val, lane, 32);
+            __syncwarp();
+        } else if (lane == 0) {
+            big_list[atomicAdd(big_ctl, 1)] = c;
+        }
+    }
+}
+
+// one block per long column (a hot gram occurs in a large share of the rows)
+__global__ void __launch_bounds__(SORT_BIG_THREADS)
+csc_sort_big_kernel(const int* __restrict__ colcnt, const int* __restrict__ colptr, const int* __restrict__ tmp_row,
+                    const float* __restrict__ tmp_val, int* __restrict__ csc_row, float* __restrict__ csc_val, int words,
+                    const int* __restrict__ big_ctl, const int* __restrict__ big_list) {
+    extern __shared__ uint32_t sort_smem[];
+    __shared__ int warp_tot[SORT_BIG_THREADS / 32];
+    uint32_t* bm = sort_smem;
+    int* pre = reinterpret_cast<int*>(bm + words);
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nbig = __ldg(big_ctl);
+    for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const int c = __ldg(big_list + b), cnt = __ldg(colcnt + c), p = __ldg(colptr + c);
+        for (int i = t; i < words; i += SORT_BIG_THREADS) bm[i] = 0u;
+        __syncthreads();
+        for (int i = t; i < cnt; i += SORT_BIG_THREADS) {
+            const int r = tmp_row[p + i];
+            atomicOr(bm + (r >> 5), 1u << (r & 31));
+        }
+        __syncthreads();
+        const int per = (words + SORT_BIG_THREADS - 1) / SORT_BIG_THREADS, lo = min(words, t * per), hi = min(words, lo + per);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += __popc(bm[i]);
+        int x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[w] = x;
+        __syncthreads();
+        int base = 0;
+        for (int i = 0; i < w; ++i) base += warp_tot[i];
+        int run = base + x - sum;
+        for (int i = lo; i < hi; ++i) { pre[i] = run; run += __popc(bm[i]); }
+        __syncthreads();
+        bitmap_rank_scatter(tmp_row, tmp_val, p, cnt, bm, pre, csc_row, csc_val, t, SORT_BIG_THREADS);
+        __syncthreads();
     }
 }
 
@@ -545,10 +656,10 @@ static void launch_adam_absent(int D, int L1, const AdamW1& ad, cudaStream_t st)
 }
 
 struct CscWorkspace {
-    int *colcnt, *done, *next_item, *heavy_ctl, *colptr, *cursor, *itemptr, *csc_row, *heavy_list;
+    int *colcnt, *done, *next_item, *heavy_ctl, *big_ctl, *colptr, *cursor, *itemptr, *csc_row, *heavy_list, *tmp_row, *big_list;
     int2* block_totals;
     int4* item_rec;
-    float* csc_val;
+    float *csc_val, *tmp_val;
     float* partial;
     size_t bytes;
 };
@@ -560,12 +671,16 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.done = a.take<int>(D + 1);
     w.next_item = a.take<int>(MAX_W1_CHUNKS);  // one work counter per column chunk; cleared together with colcnt / done
     w.heavy_ctl = a.take<int>(2);              // {heavy items, cursor}, cleared with them
+    w.big_ctl = a.take<int>(2);                // {columns queued for the block sort}, cleared with them
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
     w.itemptr = a.take<int>(D + 1);
     w.block_totals = a.take<int2>((size_t)(D + SCAN_TILE - 1) / SCAN_TILE + 1);
     w.csc_row = a.take<int>((size_t)max_nnz);
     w.csc_val = a.take<float>((size_t)max_nnz);
+    w.tmp_row = a.take<int>((size_t)max_nnz);  // segments in atomic-slot order, before the row sort
+    w.tmp_val = a.take<float>((size_t)max_nnz);
+    w.big_list = a.take<int>((size_t)(max_nnz / SORT_WARP_MAX) + 2);  // columns with > SORT_WARP_MAX entries
     w.heavy_list = a.take<int>(2 * (size_t)(max_nnz / CSC_CHUNK) + 2);  // items of columns with > CSC_CHUNK entries
     const size_t max_items = (size_t)D + (size_t)(max_nnz / CSC_CHUNK) + 1;
     w.item_rec = a.take<int4>(max_items);
@@ -581,20 +696,16 @@ static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, 
     const int cols = col_end - col_begin;
     if (blocks > cols) blocks = cols > 0 ? cols : 1;
     const size_t smem = (size_t)(SPMM_THREADS / 32) * RING * NCH * 32 * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    static PerDeviceOnce once;
+    if (smem > 48 * 1024 && once.need())
         cudaFuncSetAttribute(dw_gather_v4_kernel<NCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     AdamW1 ad{};
     if (adam) {
         ad = *adam;
         ad.colcnt = w.colcnt;
-        static bool attr2_set = false;
-        if (!attr2_set && smem > 48 * 1024) {
+        static PerDeviceOnce once2;
+        if (smem > 48 * 1024 && once2.need())
             cudaFuncSetAttribute(dw_gather_v4_kernel<NCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr2_set = true;
-        }
     }
 #define DW_ARGS w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val, (const float4*)dH, (float4*)dW, (float4*)w.partial, w.done, \
                 w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad, w.heavy_ctl, (col_begin == 0 && col_end == D) ? w.heavy_list : nullptr
@@ -694,8 +805,27 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     const int wpb = SPMM_THREADS / 32;
     int blocks = cdiv(R, wpb);
     if (blocks > nsm * 32) blocks = nsm * 32;
-    csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.csc_row, w.csc_val);
+    csc_fill_kernel<<<blocks, SPMM_THREADS, 0, st>>>(indptr, indices, values, R, w.cursor, w.tmp_row, w.tmp_val);
     LAUNCH_CHECK("csc_fill");
+    // row-order the segments: fixed summation order in the gather (bit-reproducible dW1)
+    const int words = cdiv(R, 32);
+    const size_t per_warp = (size_t)2 * words * sizeof(uint32_t);
+    int sort_wpb = (int)(((size_t)160 << 10) / per_warp);
+    DSSM_REQUIRE(sort_wpb >= 1, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_csc_build: R=%d rows exceed the row-bitmap sort (max %d)", R, (int)(((size_t)160 << 10) * 4));
+    if (sort_wpb > SPMM_THREADS / 32) sort_wpb = SPMM_THREADS / 32;
+    static PerDeviceOnce once;
+    if (once.need()) {
+        CUDA_TRY(cudaFuncSetAttribute(csc_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
+        CUDA_TRY(cudaFuncSetAttribute(csc_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
+    }
+    int sblocks = cdiv(D, sort_wpb);
+    if (sblocks > nsm * 8) sblocks = nsm * 8;
+    csc_sort_small_kernel<<<sblocks, sort_wpb * 32, (size_t)sort_wpb * per_warp, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row,
+                                                                                      w.csc_val, D, words, w.big_ctl, w.big_list);
+    LAUNCH_CHECK("csc_sort_small");
+    csc_sort_big_kernel<<<nsm, SORT_BIG_THREADS, per_warp, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row, w.csc_val, words,
+                                                                 w.big_ctl, w.big_list);
+    LAUNCH_CHECK("csc_sort_big");
     return DSSM_OK;
 }
 

@@ -365,11 +365,11 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     cudaStream_t st = (cudaStream_t)stream;
     tkc::Ws w = tkc::carve(workspace, nq, nd, k);
     const int nq_pad = (nq + tkc::QT - 1) / tkc::QT * tkc::QT;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     const size_t smem = 3 * (size_t)tkc::TILE_BYTES + (size_t)tkc::THREADS * 32 * sizeof(float) + 1024;
-    if (!attr_set) {
+    if (once.need()) {
         CUDA_TRY(cudaFuncSetAttribute(tkc::topk_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     int rc = topk_row_norms(Q, nq, d, w.qn, st);
     if (rc != DSSM_OK) return rc;
@@ -384,11 +384,6 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     if (rc != DSSM_OK) return rc;
     const size_t seed_smem = (size_t)4 * 2 * k * sizeof(float);
     const size_t sel_smem = seed_smem + (size_t)4 * 33 * (d + 1) * sizeof(float);  // lists + per-warp row staging
-    static bool attr2_set = false;
-    if (!attr2_set) {
-        CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr2_set = true;
-    }
     // thresholds from the seed (no candidates yet)
     tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt,
                                                                        w.run_s, w.run_i, w.run_cnt, w.tq);

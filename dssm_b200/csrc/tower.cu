@@ -24,8 +24,24 @@ extern thread_local cudaEvent_t g_spmm_bwd_mid_event;
 extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx);
 extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, void* img, dssm_stream_t stream);
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
-                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, dssm_stream_t stream);
-extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, dssm_stream_t stream);
+                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes, dssm_stream_t stream);
+extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes, dssm_stream_t stream);
+static inline bool is_tc_mode(int mode) { return mode == DSSM_GEMM_TC_3XTF32 || mode == DSSM_GEMM_TC_TF32; }
+static inline int tc_passes_of(int mode) { return mode == DSSM_GEMM_TC_TF32 ? 1 : 3; }
+// the two passes of the BN backward (bn.cu) and the SyncBN exchange between replicas (nvlink.cu)
+extern "C" int dssm_bn_bwd_reduce_only(const float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act, const float* gamma,
+                                       const float* mean, const float* rstd, const float* scale, const float* shift, float* dgamma,
+                                       float* dbeta, float* db, float* sumx, void* workspace, size_t workspace_bytes, dssm_stream_t stream);
+extern "C" int dssm_bn_bwd_apply_only(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act, const float* gamma,
+                                      const float* mean, const float* rstd, const float* scale, const float* shift, const float* dgamma,
+                                      const float* dbeta, dssm_stream_t stream);
+extern "C" size_t dssm_syncbn_buffer_bytes(int32_t n_ranks, int32_t n_points, int32_t Lmax);
+extern "C" int dssm_syncbn_forward(void* const* peer_bufs, int32_t n_ranks, int32_t self, int32_t point, int32_t Lmax, int32_t L,
+                                   const float* gamma, const float* beta, float* ema_mean, float* ema_var, float* mean, float* var,
+                                   float* rstd, float* scale, float* shift, float eps, float decay, int32_t update_ema, dssm_stream_t stream);
+extern "C" int dssm_syncbn_backward(void* const* peer_bufs, int32_t n_ranks, int32_t self, int32_t point, int32_t Lmax, int32_t L,
+                                    int32_t n_q, int32_t n_d, const float* gamma, const float* rstd, const float* sumx, float* dgamma,
+                                    float* dbeta, float* db, dssm_stream_t stream);
 namespace dssm {
 
 __global__ void stamp_kernel(unsigned long long* slot) {
@@ -93,6 +109,10 @@ struct dssm_tower {
     float* dh[DSSM_MAX_LAYERS + 1];
     float *bn_mean[DSSM_MAX_LAYERS + 1], *bn_var[DSSM_MAX_LAYERS + 1], *bn_rstd[DSSM_MAX_LAYERS + 1],
         *bn_scale[DSSM_MAX_LAYERS + 1], *bn_shift[DSSM_MAX_LAYERS + 1];
+    float* bn_sumx[DSSM_MAX_LAYERS + 1];  // [2][L] sum of xhat per BN instance (SyncBN backward)
+    // SyncBN: global-batch moments over n replicas (dssm_tower_set_syncbn); 0 / 1 = per-replica moments
+    int sync_n, sync_rank;
+    void* sync_bufs[DSSM_MAX_PEERS];
     float *Y, *qnorm, *dnorm, *cos_raw, *cos_sim, *prob, *loss_terms, *loss;
     void* img_fwd[DSSM_MAX_LAYERS + 1];  // pre-split weight images of layer l (tensor-core mode), rebuilt every step
     void* img_dx[DSSM_MAX_LAYERS + 1];
@@ -167,6 +187,7 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
                 *arrs[i] = a.take<float>((size_t)2 * t->L[l]);
                 reg(pre + nm[i], *arrs[i], 2, t->L[l]);
             }
+            t->bn_sumx[l] = a.take<float>((size_t)2 * t->L[l]);
         }
     }
     const int Ll = t->L[n];
@@ -207,7 +228,7 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     t->fc_ws = a.take<char>(fcw ? fcw : 256);
     for (int l = 2; l <= n; ++l) {
         t->img_fwd[l] = t->img_dx[l] = nullptr;
-        if (t->cfg.gemm_mode == DSSM_GEMM_TC_3XTF32) {
+        if (is_tc_mode(t->cfg.gemm_mode)) {
             t->img_fwd[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 0));
             t->img_dx[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 1));
         }
@@ -222,7 +243,7 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     DSSM_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= DSSM_MAX_LAYERS, DSSM_ERR_BAD_ARG, "dssm_tower_create: n_layers=%d out of [1,%d]", cfg->n_layers, DSSM_MAX_LAYERS);
     DSSM_REQUIRE(cfg->TRIGRAM_D > 0 && cfg->NEG > 0 && cfg->query_BS > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: TRIGRAM_D, NEG, query_BS must be positive");
     DSSM_REQUIRE(cfg->act == DSSM_ACT_RELU || cfg->act == DSSM_ACT_TANH || cfg->act == DSSM_ACT_NONE, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown act %d", cfg->act);
-    DSSM_REQUIRE(cfg->gemm_mode == DSSM_GEMM_FP32 || cfg->gemm_mode == DSSM_GEMM_TC_3XTF32, DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown gemm_mode %d", cfg->gemm_mode);
+    DSSM_REQUIRE(cfg->gemm_mode == DSSM_GEMM_FP32 || is_tc_mode(cfg->gemm_mode), DSSM_ERR_BAD_ARG, "dssm_tower_create: unknown gemm_mode %d", cfg->gemm_mode);
     for (int l = 0; l < cfg->n_layers; ++l)
         DSSM_REQUIRE(cfg->layers[l] > 0, DSSM_ERR_BAD_ARG, "dssm_tower_create: layer %d width %d", l + 1, cfg->layers[l]);
     const int64_t rows = (int64_t)(2 + cfg->NEG) * cfg->query_BS;
@@ -277,6 +298,8 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->img_forked = false;
     t->launches = 0;
     t->fuse_w1_adam = false;
+    t->sync_n = 0;
+    t->sync_rank = 0;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
     return DSSM_OK;
@@ -383,11 +406,49 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     return DSSM_OK;
 }
 
+extern "C" size_t dssm_tower_syncbn_bytes(const dssm_tower* t, int32_t n_ranks) {
+    if (!t || n_ranks < 1 || n_ranks > DSSM_MAX_PEERS) return 0;
+    int m = 0;
+    for (int l = 1; l <= t->n_layers; ++l) m = t->L[l] > m ? t->L[l] : m;
+    return dssm_syncbn_buffer_bytes(n_ranks, 2 * t->n_layers, m);
+}
+
+extern "C" int dssm_tower_set_syncbn(dssm_tower* t, int32_t n_ranks, int32_t rank, void* const* host_peer_bufs) {
+    DSSM_REQUIRE(t, DSSM_ERR_BAD_ARG, "dssm_tower_set_syncbn: null tower");
+    // captured graphs hold the previous mode's launches
+    if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+    if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+    if (t->graph_dp_exec) { cudaGraphExecDestroy(t->graph_dp_exec); t->graph_dp_exec = nullptr; }
+    if (t->graph_dp) { cudaGraphDestroy(t->graph_dp); t->graph_dp = nullptr; }
+    if (n_ranks <= 1) {
+        t->sync_n = 0;
+        return DSSM_OK;
+    }
+    DSSM_REQUIRE(t->cfg.use_bn, DSSM_ERR_STATE, "dssm_tower_set_syncbn: the tower has no BatchNorm");
+    DSSM_REQUIRE(n_ranks <= DSSM_MAX_PEERS && rank >= 0 && rank < n_ranks && host_peer_bufs, DSSM_ERR_BAD_ARG,
+                 "dssm_tower_set_syncbn: n_ranks=%d rank=%d (at most %d peers)", n_ranks, rank, DSSM_MAX_PEERS);
+    for (int l = 1; l <= t->n_layers; ++l)
+        DSSM_REQUIRE(t->L[l] <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_tower_set_syncbn: layer width %d > 1024", t->L[l]);
+    for (int r = 0; r < n_ranks; ++r) {
+        DSSM_REQUIRE(host_peer_bufs[r] && aligned16(host_peer_bufs[r]), DSSM_ERR_BAD_ALIGN, "dssm_tower_set_syncbn: peer buffer %d null or unaligned", r);
+        t->sync_bufs[r] = host_peer_bufs[r];
+    }
+    t->sync_n = n_ranks;
+    t->sync_rank = rank;
+    return DSSM_OK;
+}
+
 #define TRY(call)                  \
     do {                           \
         int _rc = (call);          \
         if (_rc != DSSM_OK) return _rc; \
     } while (0)
+
+static int max_width(const dssm_tower* t) {
+    int m = 0;
+    for (int l = 1; l <= t->n_layers; ++l) m = t->L[l] > m ? t->L[l] : m;
+    return m;
+}
 
 static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_t* indices, const float* values,
                               int on_train, int update_ema, bool want_grad, dssm_stream_t s) {
@@ -397,7 +458,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     markf("start");
     t->csc_forked = false;
     t->img_forked = false;
-    const bool tc = c.gemm_mode == DSSM_GEMM_TC_3XTF32 && n >= 2;
+    const bool tc = is_tc_mode(c.gemm_mode) && n >= 2;
     const bool timing = g_timer && g_timer->on && g_timer->serial;
     const bool train = want_grad && on_train;
     const bool fork_csc = train && t->L[1] % 4 == 0 && t->L[1] <= 1024 && !timing;
@@ -447,10 +508,16 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     for (int l = 1; l <= n; ++l) {
         const std::string ls = std::to_string(l);
         if (c.use_bn) {
-            TRY(dssm_bn_forward(t->h[l], R, t->L[l], B, on_train, update_ema, t->P_("bn" + ls + "_gamma"),
+            const bool sync = t->sync_n > 1 && on_train;  // the shadows then move with the GLOBAL moments, in the exchange kernel
+            TRY(dssm_bn_forward(t->h[l], R, t->L[l], B, on_train, sync ? 0 : update_ema, t->P_("bn" + ls + "_gamma"),
                                 t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
                                 c.bn_eps, c.ema_decay, t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l],
                                 t->bn_shift[l], t->bn_ws, t->bn_ws_bytes, s));
+            if (sync)
+                TRY(dssm_syncbn_forward(t->sync_bufs, t->sync_n, t->sync_rank, l - 1, max_width(t), t->L[l], t->P_("bn" + ls + "_gamma"),
+                                        t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
+                                        t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l], t->bn_shift[l], c.bn_eps, c.ema_decay,
+                                        update_ema, s));
             markf("bn_fwd" + ls);
         }
         const float* sc = c.use_bn ? t->bn_scale[l] : nullptr;
@@ -459,7 +526,7 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
             const std::string ns = std::to_string(l + 1);
             if (tc && t->L[l] % 4 == 0 && t->L[l + 1] % 4 == 0) {
                 TRY(dssm_fc_fwd_tc_img(t->h[l], R, t->L[l], B, sc, sh, c.act, t->img_fwd[l + 1], t->P_("b" + ns), t->L[l + 1],
-                                       t->h[l + 1], s));
+                                       t->h[l + 1], tc_passes_of(c.gemm_mode), s));
             } else {
                 TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
                                 t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));
@@ -492,7 +559,17 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
     const int n = t->n_layers, R = t->R, B = t->B;
     for (int l = n; l >= 1; --l) {
         const std::string ls = std::to_string(l);
-        if (c.use_bn) {
+        if (c.use_bn && t->sync_n > 1) {
+            // SyncBN: local column sums -> average over the replicas (and this replica's db) -> dH with the global sums
+            TRY(dssm_bn_bwd_reduce_only(t->dh[l], t->h[l], R, t->L[l], B, c.act, t->P_("bn" + ls + "_gamma"), t->bn_mean[l], t->bn_rstd[l],
+                                        t->bn_scale[l], t->bn_shift[l], t->G_("bn" + ls + "_gamma"), t->G_("bn" + ls + "_beta"), nullptr,
+                                        t->bn_sumx[l], t->bn_ws, t->bn_ws_bytes, s));
+            TRY(dssm_syncbn_backward(t->sync_bufs, t->sync_n, t->sync_rank, n + l - 1, max_width(t), t->L[l], B, R - B,
+                                     t->P_("bn" + ls + "_gamma"), t->bn_rstd[l], t->bn_sumx[l], t->G_("bn" + ls + "_gamma"),
+                                     t->G_("bn" + ls + "_beta"), t->G_("b" + ls), s));
+            TRY(dssm_bn_bwd_apply_only(t->dh[l], t->h[l], R, t->L[l], B, c.act, t->P_("bn" + ls + "_gamma"), t->bn_mean[l], t->bn_rstd[l],
+                                       t->bn_scale[l], t->bn_shift[l], t->G_("bn" + ls + "_gamma"), t->G_("bn" + ls + "_beta"), s));
+        } else if (c.use_bn) {
             TRY(dssm_bn_act_backward(t->dh[l], t->h[l], R, t->L[l], B, c.act, t->P_("bn" + ls + "_gamma"), t->bn_mean[l],
                                      t->bn_rstd[l], t->bn_scale[l], t->bn_shift[l], t->G_("bn" + ls + "_gamma"),
                                      t->G_("bn" + ls + "_beta"), t->G_("b" + ls), t->bn_ws, t->bn_ws_bytes, s));
@@ -508,8 +585,8 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
                                c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
             markf("fc_dw" + ls);
-            if (c.gemm_mode == DSSM_GEMM_TC_3XTF32 && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
-                TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], s));
+            if (is_tc_mode(c.gemm_mode) && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
+                TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], tc_passes_of(c.gemm_mode), s));
             } else {
                 TRY(dssm_fc_bwd_dx(t->dh[l], R, t->L[l], t->P_("W" + ls), t->L[l - 1], t->dh[l - 1], c.gemm_mode, t->fc_ws,
                                    t->fc_ws_bytes, s));

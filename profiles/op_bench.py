@@ -1,6 +1,6 @@
 """Warm-cache duration of the individual kernels of the dense stack at a config's shapes: G launches of one op are
 captured into a CUDA graph and replayed, so the figure is kernel time + the ~1 us node-to-node gap, with the operands
-L2-resident as they are inside the real step.   python profiles/op_bench.py [C2|C3|C4]"""
+L2-resident as they are inside the real step.   python profiles/op_bench.py [C2|C3|C4] [3|1]"""
 import ctypes as C
 import sys
 import torch
@@ -11,6 +11,7 @@ from dssm_b200.synthetic import make_batch
 from dssm_b200 import ops
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
+PASSES = int(sys.argv[2]) if len(sys.argv) > 2 else 3  # 3 = 3xTF32 (parity mode), 1 = single-pass tf32
 conf = baseline_config(name)
 B, R = conf.query_BS, (2 + conf.NEG) * conf.query_BS
 dev = torch.device("cuda")
@@ -42,8 +43,8 @@ for fn_name, args in (("dssm_fc_tc_image_bytes", None), ("dssm_fc_tc_build_image
 i32, vp = C.c_int32, C.c_void_p
 lib.dssm_fc_tc_image_bytes.argtypes = [i32, i32, i32]
 lib.dssm_fc_tc_build_image.argtypes = [vp, i32, i32, i32, vp, vp]
-lib.dssm_fc_fwd_tc_img.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, vp]
-lib.dssm_fc_bwd_dx_tc_img.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+lib.dssm_fc_fwd_tc_img.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp]
+lib.dssm_fc_bwd_dx_tc_img.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp]
 
 dims = [conf.TRIGRAM_D] + list(conf.layers)
 for l in range(2, len(dims)):
@@ -55,9 +56,9 @@ for l in range(2, len(dims)):
     imgx = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 1), dtype=torch.uint8, device=dev)
     check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, p(imgf), st()))
     check(lib.dssm_fc_tc_build_image(p(W), K, N, 1, p(imgx), st()))
-    bench(f"fc_fwd  tc img  [{R}x{K}]x[{K}x{N}]", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), st())),
+    bench(f"fc_fwd  tc img  [{R}x{K}]x[{K}x{N}]", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), PASSES, st())),
           4 * R * (K + N))
-    bench(f"fc_dx   tc img  [{R}x{N}]x[{N}x{K}]", lambda: check(lib.dssm_fc_bwd_dx_tc_img(p(dH), R, N, p(imgx), K, p(dA), st())), 4 * R * (K + N))
+    bench(f"fc_dx   tc img  [{R}x{N}]x[{N}x{K}]", lambda: check(lib.dssm_fc_bwd_dx_tc_img(p(dH), R, N, p(imgx), K, p(dA), PASSES, st())), 4 * R * (K + N))
     ws = torch.zeros(lib.dssm_fc_bwd_dw_workspace_bytes(R, K, N), dtype=torch.uint8, device=dev)
     dW, db = f32(K, N), f32(N)
     bench(f"fc_dw   tc      [{K}x{R}]x[{R}x{N}] (+reduce)",
