@@ -83,6 +83,14 @@ class HostBatchLoader:
         self._bufs = [(mk(self.R + 1, torch.int32), mk(max(self.max_nnz, 1), torch.int32), mk(max(self.max_nnz, 1), torch.float32))
                       for _ in range(self.depth)]
 
+    @classmethod
+    def from_texts(cls, vectorizer, queries: Sequence[str], docs: Sequence[str], neg_docs: Sequence[str], query_BS: int, NEG: int,
+                   **kw) -> "HostBatchLoader":
+        """The reference's path from text to batches (new_dssm.py:33-43): the fitted vectorizer -- a
+        dssm_b200.vectorizer.CountVectorizerCompat or sklearn's CountVectorizer -- transforms the three text lists into the
+        epoch matrices this loader slices; int64 term counts are cast to float32 when a batch is assembled, as the feed does."""
+        return cls(vectorizer.transform(queries), vectorizer.transform(docs), vectorizer.transform(neg_docs), query_BS, NEG, **kw)
+
     def _parts(self, b: int):
         B, N = self.B, self.NEG
         return ((self.q, b * B, (b + 1) * B), (self.p, b * B, (b + 1) * B), (self.n, b * B * N, (b + 1) * B * N))

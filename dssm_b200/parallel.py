@@ -33,6 +33,13 @@ def shard_stacked_batch(b: StackedBatch, query_BS_global: int, NEG: int, rank: i
     return StackedBatch(Y.indptr.astype(np.int32), Y.indices.astype(np.int32), Y.data.astype(np.float32), b.n_cols)
 
 
+def _all_ranks_agree(flag: bool, device, group=None) -> bool:
+    """True iff `flag` is true on EVERY rank (all-reduce MIN): mode decisions must be taken together."""
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
 def allreduce_mean_(tensors: List[torch.Tensor], group=None) -> None:
     """In-place mean over ranks (sum all-reduce, then scale).  Works on NCCL (GPU) and gloo (CPU tests)."""
     world = dist.get_world_size(group)
@@ -50,7 +57,8 @@ class DataParallelTower:
     capture_graph() records the whole step -- kernels and collectives -- into one CUDA graph, so the ~60 launches
     cost no CPU time per step."""
 
-    def __init__(self, tower, group=None, n_chunks: int = 2, comm: str = "nccl", multicast: Optional[bool] = None):
+    def __init__(self, tower, group=None, n_chunks: int = 2, comm: str = "nccl", multicast: Optional[bool] = None,
+                 sync_bn: bool = False):
         if comm not in ("nccl", "nvlink"):
             raise ValueError("comm must be 'nccl' or 'nvlink'")
         self.tower = tower
@@ -58,24 +66,45 @@ class DataParallelTower:
         self.comm = comm
         self.multicast = multicast  # None: use NVSwitch multicast (NVLS) when the symmetric-memory handle offers it
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_chunks = max(1, min(int(n_chunks), 64))
         off, rows, cols = tower._layout[0]["W1"]
         self.w1_end = off + ((rows * cols + 3) // 4) * 4
         self.pipelined = tower.conf.layers[0] % 4 == 0 and off == 0
         self.graph = None
         self.graphed = False
-        # identical starting parameters on every rank
+        self.sync_bn = False
+        # identical starting state on every rank: parameters AND optimizer state (Adam m, v, beta powers) AND the EMA
+        # shadows -- rank 0 may have restored a checkpoint; replicas whose slots differ would apply different updates to
+        # the same averaged gradient and drift apart silently
         if self.world > 1:
-            dist.broadcast(tower.params, src=0, group=group)
+            for buf in (tower.params, tower.m, tower.v, tower.beta_pow, tower.ema):
+                dist.broadcast(buf, src=0, group=group)
         if comm == "nvlink" and self.world > 1:
-            try:
-                self._setup_nvlink()
-            except (RuntimeError, ImportError) as e:  # no peer mapping on this box / torch build: use NCCL, loudly
+            # the choice of exchange must be COLLECTIVE: a rank that fell back to NCCL alone would wait in an all-reduce
+            # while the others wait in the symmetric-memory rendezvous
+            ok, why = True, ""
+            if not (self.pipelined and getattr(tower, "symmetric", False)):
+                ok, why = False, "needs DSSMTower(..., symmetric=True) and an FC1 width that is a multiple of 4"
+            if self.world > 16:
+                ok, why = False, "addresses at most 16 peers"
+            if not _all_ranks_agree(ok, tower.device, group):
+                ok = False
+            if ok:
+                try:
+                    self._setup_nvlink()
+                except (RuntimeError, ImportError) as e:  # rendezvous itself is collective: it fails on every rank or none
+                    ok, why = False, f"{type(e).__name__}: {e}"
+                if not _all_ranks_agree(ok, tower.device, group):
+                    ok = False
+            if not ok:
                 import sys
 
-                print(f"[dssm_b200] NVLink peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce",
-                      file=sys.stderr)
+                print(f"[dssm_b200] rank {self.rank}: NVLink peer-memory exchange unavailable ({why or 'another rank cannot use it'}); "
+                      "all ranks use the NCCL all-reduce", file=sys.stderr)
                 self.comm = "nccl"
+        if sync_bn and self.world > 1:
+            self._setup_syncbn()
 
     # ---- NVLink peer-memory exchange of dW1 (csrc/nvlink.cu) --------------------------------------------------
     def _setup_nvlink(self) -> None:
@@ -92,7 +121,6 @@ class DataParallelTower:
         if self.world > 16:
             raise ValueError("comm='nvlink' addresses at most 16 peers")
         grp = self.group if self.group is not None else dist.group.WORLD
-        self.rank = dist.get_rank(grp)
         self._h_params = symm_mem.rendezvous(t.params, grp)
         self._h_comm = symm_mem.rendezvous(t.comm, grp)
         w1_off = t._layout[0]["W1"][0]  # 0 (checked by self.pipelined)
@@ -116,6 +144,59 @@ class DataParallelTower:
         D = t.conf.TRIGRAM_D
         per = (D + self.world - 1) // self.world
         self.row_begin, self.row_end = min(self.rank * per, D), min((self.rank + 1) * per, D)
+
+    # ---- SyncBN: global-batch BatchNorm moments (csrc/nvlink.cu: syncbn_fwd_kernel / syncbn_bwd_kernel) ------------------
+    def _setup_syncbn(self) -> None:
+        """A small peer-mapped exchange buffer per rank (flags + one slot per BN layer, direction and rank); the tower's
+        training-mode BN then uses the moments of the GLOBAL batch (what the single-process reference computes over n*B
+        groups, new_dssm.py:77) and the backward averages [dbeta | dgamma] over the replicas: n replicas at B groups each
+        reproduce the reference step at n*B (oracle/syncbn.py is the specification)."""
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import check, lib
+
+        t = self.tower
+        if not t.conf.use_bn:
+            return
+        grp = self.group if self.group is not None else dist.group.WORLD
+        nbytes = lib.dssm_tower_syncbn_bytes(t._h, self.world)
+        self._sync_buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=t.device).zero_()
+        self._h_sync = symm_mem.rendezvous(self._sync_buf, grp)
+        torch.cuda.synchronize(t.device)
+        dist.barrier(group=self.group)  # every rank's buffer is zero before anybody's first flag can land in it
+        arr = (C.c_void_p * self.world)(*[int(p) for p in self._h_sync.buffer_ptrs])
+        check(lib.dssm_tower_set_syncbn(t._h, self.world, self.rank, arr))
+        self.sync_bn = True
+
+    # ---- checkpointing under sharded Adam ---------------------------------------------------------------------
+    def state_dict(self):
+        """tower.state_dict() made whole: with comm='nvlink' each rank runs Adam only on the W1 rows it owns, so its m / v
+        are current for those rows only.  Every rank gathers the owners' row blocks first (all ranks must call this)."""
+        t = self.tower
+        if self.comm == "nvlink" and self.world > 1:
+            L1 = t.conf.layers[0]
+            D = t.conf.TRIGRAM_D
+            per = (D + self.world - 1) // self.world
+            for buf in (t.m, t.v):
+                w = buf[:D * L1].view(D, L1)
+                for r in range(self.world):
+                    lo, hi = min(r * per, D), min((r + 1) * per, D)
+                    if hi > lo:
+                        dist.broadcast(w[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                       group=self.group)
+        return t.state_dict()
+
+    def save(self, path: str, vocabulary=None):
+        """Collective: gathers the sharded optimizer state on every rank, rank 0 writes the file."""
+        sd = self.state_dict()
+        out = None
+        if self.rank == 0:
+            out = self.tower.save(path, vocabulary=vocabulary, state=sd)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return out
 
     def _step_staged_nvlink(self) -> None:
         from ._lib import check, lib, ptr, stream_ptr

@@ -67,14 +67,35 @@ def shard_range(n_docs: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n_docs, lo + per)
 
 
-def sharded_corpus_topk(Q: torch.Tensor, local_docs: torch.Tensor, k: int, id_offset: int, group=None):
-    """Every rank: local top-k over its shard, NCCL all-gather of the (scores, ids) lists, merge on every rank."""
-    s, i = corpus_topk(Q, local_docs, k, id_offset)
+PAD_ID = 0x7FFFFFFF  # id of a padding entry in a local list: loses every (score desc, id asc) comparison against a real doc
+
+
+def sharded_corpus_topk(Q: torch.Tensor, local_docs: torch.Tensor, k: int, id_offset: int, group=None,
+                        total_docs: Optional[int] = None, method: str = "auto"):
+    """Every rank: local top-k over its shard, NCCL all-gather of the (scores, ids) lists, merge on every rank.
+    The local stage ALWAYS yields [nq, k]: a shard with fewer than k documents (shard_range gives the last rank a short or
+    even empty one) pads its lists with (-inf, PAD_ID), which the merge ranks behind every real document, so the gathered
+    shapes agree on all ranks; the result is cut to min(k, total_docs) columns (total_docs: corpus size over all shards;
+    None = all-reduced here)."""
+    nq = Q.shape[0]
+    nd_local = int(local_docs.shape[0])
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return s, i
-    gs = torch.empty((world,) + tuple(s.shape), dtype=s.dtype, device=s.device)
-    gi = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+        return corpus_topk(Q, local_docs, k, id_offset, method=method)
+    s = torch.full((nq, k), float("-inf"), dtype=torch.float32, device=Q.device)
+    i = torch.full((nq, k), PAD_ID, dtype=torch.int32, device=Q.device)
+    if nd_local > 0:
+        ls, li = corpus_topk(Q, local_docs, min(k, nd_local), id_offset, method=method)
+        s[:, :ls.shape[1]] = ls
+        i[:, :li.shape[1]] = li
+    if total_docs is None:
+        t = torch.tensor([nd_local], dtype=torch.int64, device=Q.device)
+        dist.all_reduce(t, group=group)
+        total_docs = int(t.item())
+    gs = torch.empty((world, nq, k), dtype=s.dtype, device=s.device)
+    gi = torch.empty((world, nq, k), dtype=i.dtype, device=i.device)
     dist.all_gather_into_tensor(gs, s, group=group)
     dist.all_gather_into_tensor(gi, i, group=group)
-    return topk_merge(gs, gi)
+    ms, mi = topk_merge(gs, gi)
+    kk = min(k, total_docs)
+    return (ms[:, :kk].contiguous(), mi[:, :kk].contiguous()) if kk < k else (ms, mi)

@@ -138,8 +138,12 @@ class DSSMTower:
             return self.tensor("Y")[2 * B:]
         if key == "hit_prob":
             return self.tensor("prob")[:, 0:1]
-        if key == "accuracy":  # new_dssm.py:220-221
-            return (torch.argmax(self.tensor("prob"), dim=1) == 0).float().mean()
+        if key == "accuracy":  # new_dssm.py:220-221, on the device (csrc/metrics.cu)
+            if getattr(self, "_acc_out", None) is None:
+                self._acc_out = torch.zeros(1, dtype=torch.float32, device=self.device)
+            prob = self.tensor("prob")
+            check(lib.dssm_accuracy(ptr(prob), prob.shape[0], prob.shape[1], ptr(self._acc_out), stream_ptr()))
+            return self._acc_out[0]
         if key in self._layout[0]:
             return self.param(key)
         if key in self._layout[1]:
@@ -194,6 +198,75 @@ class DSSMTower:
         sd["beta_pow"] = self.beta_pow.cpu().numpy().copy()
         return sd
 
+    # ---- on-disk checkpoint (the reference: tf.train.Saver().save(sess, "model/model_1.ckpt"), new_dssm.py:248,331;
+    #      vocabulary pickled beside it, utils/utils.py:241-261) ------------------------------------------------------
+    CKPT_FORMAT = "dssm_b200.ckpt.v1"
+
+    def save(self, path: str, vocabulary: Optional[Dict[str, int]] = None, state: Optional[Dict[str, np.ndarray]] = None) -> str:
+        """Write everything tf.train.Saver() holds for this graph -- the 12 trainables (W{l}, b{l}, bn{l}_{q|d}_{beta|gamma}),
+        the 8 EMA shadows, the Adam slots m / v of every trainable and the two beta powers -- plus the hyper-parameters and,
+        optionally, the fitted vocabulary (token -> column, what the reference pickles as output/vectorizer_data) into ONE
+        .npz file (TF's V2 checkpoint files cannot be written without TF; the variable SET is the reference's).  Returns the
+        path written.  `state`: a state dict to write instead of this tower's (DataParallelTower.state_dict())."""
+        import json
+
+        sd = dict(state if state is not None else self.state_dict())
+        c = self.conf
+        meta = {"format": self.CKPT_FORMAT, "TRIGRAM_D": c.TRIGRAM_D, "layers": list(c.layers), "NEG": c.NEG, "query_BS": c.query_BS,
+                "learning_rate": c.learning_rate, "use_bn": c.use_bn, "act": c.act, "loss_eps": c.loss_eps, "loss_div_bs": c.loss_div_bs,
+                "bn_eps": c.bn_eps, "ema_decay": c.ema_decay, "gamma": c.gamma, "beta1": c.beta1, "beta2": c.beta2, "adam_eps": c.adam_eps}
+        sd["__meta__"] = np.frombuffer(json.dumps(meta).encode("utf-8"), dtype=np.uint8)
+        if vocabulary is not None:
+            toks = sorted(vocabulary, key=lambda k: vocabulary[k])
+            sd["__vocab_tokens__"] = np.frombuffer("\n".join(toks).encode("utf-8"), dtype=np.uint8)
+            sd["__vocab_ids__"] = np.asarray([vocabulary[k] for k in toks], dtype=np.int64)
+        if not path.endswith(".npz"):
+            path = path + ".npz"
+        with open(path, "wb") as f:
+            np.savez(f, **sd)
+        return path
+
+    @staticmethod
+    def read_checkpoint(path: str):
+        """(state dict, meta dict, vocabulary or None) of a file written by save()."""
+        import json
+
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        meta = json.loads(bytes(z["__meta__"]).decode("utf-8"))
+        if meta.get("format") != DSSMTower.CKPT_FORMAT:
+            raise ValueError(f"{path}: not a {DSSMTower.CKPT_FORMAT} checkpoint")
+        vocab = None
+        if "__vocab_tokens__" in z.files:
+            toks = bytes(z["__vocab_tokens__"]).decode("utf-8").split("\n")
+            vocab = {t: int(i) for t, i in zip(toks, z["__vocab_ids__"])}
+        sd = {k: z[k] for k in z.files if not k.startswith("__")}
+        return sd, meta, vocab
+
+    def restore(self, path: str) -> Optional[Dict[str, int]]:
+        """saver.restore(sess, ckpt) (load_model_and_save_vector.py:10-11): loads parameters, EMA shadows and optimizer state;
+        refuses a checkpoint of a different graph.  Returns the stored vocabulary (or None)."""
+        sd, meta, vocab = self.read_checkpoint(path)
+        c = self.conf
+        if int(meta["TRIGRAM_D"]) != c.TRIGRAM_D or tuple(meta["layers"]) != tuple(c.layers) or bool(meta["use_bn"]) != c.use_bn:
+            raise ValueError(f"{path}: checkpoint of TRIGRAM_D={meta['TRIGRAM_D']} layers={meta['layers']} use_bn={meta['use_bn']} "
+                             f"does not fit this tower (TRIGRAM_D={c.TRIGRAM_D} layers={list(c.layers)} use_bn={c.use_bn})")
+        self.load_state_dict(sd)
+        return vocab
+
+    @classmethod
+    def from_checkpoint(cls, path: str, max_nnz: int, device="cuda", query_BS: Optional[int] = None, NEG: Optional[int] = None,
+                        gemm_mode: str = "fp32", **kw):
+        """Build a tower of the checkpoint's graph (the import_meta_graph + restore pair of load_model_and_save_vector.py:10-11).
+        query_BS / NEG may differ from training time: they only shape the batch."""
+        sd, meta, vocab = cls.read_checkpoint(path)
+        conf = Config(TRIGRAM_D=int(meta["TRIGRAM_D"]), query_BS=int(query_BS or meta["query_BS"]), NEG=int(NEG or meta["NEG"]),
+                      learning_rate=float(meta["learning_rate"]), layers=tuple(meta["layers"]), use_bn=bool(meta["use_bn"]),
+                      act=meta["act"], loss_eps=float(meta["loss_eps"]), loss_div_bs=bool(meta["loss_div_bs"]), gemm_mode=gemm_mode)
+        t = cls(conf, max_nnz=max_nnz, device=device, **kw)
+        t.load_state_dict(sd)
+        t.vocabulary = vocab
+        return t
+
     def load_state_dict(self, sd: Dict[str, np.ndarray]) -> None:
         self.load_params({k[len("params/"):]: v for k, v in sd.items() if k.startswith("params/")})
         n = len(self.conf.layers)
@@ -231,6 +304,15 @@ class DSSMTower:
         check(lib.dssm_tower_forward(self._h, ptr(x.indptr), ptr(x.indices), ptr(x.values), int(on_train), int(ue), stream_ptr()))
         self._last = x  # keep the CSR alive for backward
         return self.tensor("loss")
+
+    def eval_step(self, x: DeviceCSR, auc=None):
+        """The reference's evaluation of one batch (new_dssm.py:274-286) from ONE forward: it runs sess.run(loss),
+        sess.run(auc_op) and sess.run(auc_value) -- three full forwards with on_train=False; here the inference-mode forward
+        runs once, the streaming AUC (a dssm_b200.DeviceStreamingAUC) is updated on the device from the same cos_sim_raw
+        and nothing is copied to the host.  Returns (loss, auc) as device scalars (auc None without a metric)."""
+        loss = self.forward(x, on_train=False)
+        a = auc.update(self.tensor("cos_sim_raw"), self.conf.query_BS) if auc is not None else None
+        return loss, a
 
     def backward(self) -> None:
         check(lib.dssm_tower_backward(self._h, stream_ptr()))
@@ -418,5 +500,16 @@ class DSSMTower:
         out = []
         for n in names:
             key = n.split("/")[-1].split(":")[0]
-            out.append(None if key == "train_step" else self.tensor(n).detach().cpu().numpy().copy())
+            if key == "train_step":
+                out.append(None)
+            elif key in ("auc_op", "update_op") or key in ("auc_value", "value"):
+                # tf.metrics.auc's (value, update_op) pair of new_dssm.py:230: accumulated on the device, never reset
+                if getattr(self, "auc", None) is None:
+                    from .export import DeviceStreamingAUC
+
+                    self.auc = DeviceStreamingAUC(self.device)
+                v = self.auc.update(self.tensor("cos_sim_raw"), self.conf.query_BS) if key in ("auc_op", "update_op") else self.auc.result()
+                out.append(np.float32(v.item()))
+            else:
+                out.append(self.tensor(n).detach().cpu().numpy().copy())
         return out[0] if single else out

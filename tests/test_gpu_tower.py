@@ -184,12 +184,13 @@ def test_host_step_graph_and_sess_run_shim():
         la = a.train_step(a.to_device(bt)).item()
         lb = b_.train_step_host(b_.pin(bt))
         lc = c.train_step_host(c.pin(bt))
-        # same kernels; only the atomic slot order inside dW1's columns differs run to run, which Adam amplifies
-        assert abs(la - lb) <= 2e-4 * abs(la) and abs(la - lc) <= 2e-4 * abs(la)
+        # same kernels, same fixed summation orders (row-ordered CSC columns, chunk-ordered BN / split-K merges): the three
+        # paths are BIT-identical
+        assert la == lb == lc, (la, lb, lc)
     pa, pb, pc = a.export_params(), b_.export_params(), c.export_params()
-    # same kernels, same order: only the atomic slot order inside dW1's columns can differ between runs
-    assert_update_close(pb, pa, params, conf.use_bn, "host path", l2_tol=2e-2)
-    assert_update_close(pc, pa, params, conf.use_bn, "graph path", l2_tol=2e-2)
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), f"host path differs in {k}"
+        assert np.array_equal(pa[k], pc[k]), f"graph path differs in {k}"
     assert c.launch_count > 0 and a.launch_count > 0
     # sess.run shim on reference-style feeds
     X = batches[0].to_scipy()
@@ -226,8 +227,10 @@ def test_pipelined_host_feed_matches_synchronous_host_steps():
     got = b_.train_epoch_host([pinned[i % 3] for i in range(7)])
     assert len(got) == len(ref)
     for i, (x, y) in enumerate(zip(ref, got)):
-        assert abs(x - y) <= 2e-4 * abs(x), f"step {i}: {x} vs {y}"
-    assert_update_close(b_.export_params(), a.export_params(), params, conf.use_bn, "pipelined feed", l2_tol=2e-2)
+        assert x == y, f"step {i}: {x} vs {y}"
+    pa, pb = a.export_params(), b_.export_params()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), f"pipelined feed differs in {k}"
     with pytest.raises(DssmError):
         b_.feed_wait(0)  # only the last two steps are waitable
     ip, ix, vl, nnz = pinned[0]
@@ -258,7 +261,7 @@ def test_host_batch_loader_drives_the_pipelined_feed():
     got = b_.train_epoch_host(loader)
     assert len(got) == len(ref)
     for i, (x, y) in enumerate(zip(ref, got)):
-        assert abs(x - y) <= 2e-4 * abs(x), f"step {i}: {x} vs {y}"
+        assert x == y, f"step {i}: {x} vs {y}"
 
 
 def test_wrong_batch_shape_is_rejected():
@@ -274,7 +277,9 @@ def test_wrong_batch_shape_is_rejected():
         t.backward()  # no preceding training forward
 
 
-def test_checkpoint_roundtrip():
+def test_checkpoint_roundtrip(tmp_path):
+    """state_dict -> load_state_dict, and save(path) -> restore(path) / from_checkpoint(path) on disk with the vocabulary
+    (new_dssm.py:248,331; utils/utils.py:241-261): training continues BIT-identically from the restored state."""
     from dssm_b200 import Config, DSSMTower
     from dssm_b200.synthetic import make_batch
 
@@ -284,14 +289,79 @@ def test_checkpoint_roundtrip():
     t = DSSMTower(conf, max_nnz=mx, seed=1)
     t.train_step(t.to_device(b[0]))
     sd = t.state_dict()
+    vocab = {f"tok{i}": i for i in range(conf.TRIGRAM_D)}
+    path = t.save(str(tmp_path / "model_1.ckpt"), vocabulary=vocab)
+    assert path.endswith(".npz")
     u = DSSMTower(conf, max_nnz=mx, seed=2)
     u.load_state_dict(sd)
+    w = DSSMTower(conf, max_nnz=mx, seed=3)
+    assert w.restore(path) == vocab
+    x_ = DSSMTower.from_checkpoint(path, max_nnz=mx)
+    assert x_.vocabulary == vocab and tuple(x_.conf.layers) == (32, 16)
     for x in b[1:]:
-        lt, lu = t.train_step(t.to_device(x)).item(), u.train_step(u.to_device(x)).item()
-        assert abs(lt - lu) <= 1e-5 * abs(lt)
-    pt, pu = t.export_params(), u.export_params()
-    init = {k: np.zeros_like(v) for k, v in pt.items()}
-    assert_update_close(pu, pt, init, conf.use_bn, "checkpoint roundtrip", l2_tol=1e-3)
+        lt = t.train_step(t.to_device(x)).item()
+        for other in (u, w, x_):
+            assert other.train_step(other.to_device(x)).item() == lt
+    pt = t.export_params()
+    for other in (u, w, x_):
+        po = other.export_params()
+        for k in pt:
+            assert np.array_equal(pt[k], po[k]), k
+        assert torch.equal(other.m, t.m) and torch.equal(other.v, t.v) and torch.equal(other.ema, t.ema)
+        assert torch.equal(other.beta_pow, t.beta_pow)
+    bad = DSSMTower(Config(TRIGRAM_D=2000, query_BS=16, NEG=3, layers=(32, 8)), max_nnz=mx)
+    with pytest.raises(ValueError):
+        bad.restore(path)
+
+
+def test_train_step_is_bit_reproducible():
+    """Two towers fed the same batches end on the same bits (the reference on TF-CPU is deterministic too): the dW1
+    gather sums every column in row order (csc_sort_*), all other reductions merge in a fixed order."""
+    from dssm_b200 import DSSMTower, baseline_config
+    from dssm_b200.synthetic import init_params, make_batch
+
+    for name, steps in (("C1", 3), ("C2", 2)):
+        conf = baseline_config(name)
+        batches = [make_batch(conf, seed=s) for s in range(steps)]
+        params = init_params(conf, 0)
+        runs = []
+        for _ in range(2):
+            t = DSSMTower(conf, max_nnz=max(b.nnz for b in batches), params=params)
+            losses = [t.train_step(t.to_device(b)).item() for b in batches]
+            runs.append((losses, t.params.clone(), t.m.clone(), t.v.clone()))
+        assert runs[0][0] == runs[1][0]
+        for a_, b_ in zip(runs[0][1:], runs[1][1:]):
+            assert torch.equal(a_, b_)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_tf32_mode_tolerance(name):
+    """DSSM_GEMM_TC_TF32 (one tf32 MMA per product) against the float64 oracle: the tolerance quoted in include/dssm_b200.h
+    and DESIGN.md is measured HERE.  Forward tensors are compared relative to their scale."""
+    from dssm_b200 import DSSMTower, baseline_config
+    from dssm_b200.synthetic import init_params, lambdas_for, make_batch
+    from oracle import DSSMOracle
+
+    conf = baseline_config(name, "tc_tf32")
+    lq, ld = lambdas_for(conf)
+    b = make_batch(conf, seed=3, lam_query=lq, lam_doc=ld)
+    params = init_params(conf, 0)
+    t = DSSMTower(conf, max_nnz=b.nnz, params=params)
+    loss = t.forward(t.to_device(b), on_train=True).item()
+    o64 = DSSMOracle(oracle_config(conf), params, dtype=np.float64)
+    c = o64.forward(b.to_scipy(), on_train=True, update_ema=False)
+    e_loss = abs(loss - float(c["loss"])) / abs(float(c["loss"]))
+    e_y = rel_err(t.tensor("Y").cpu().numpy(), c["Y"])
+    e_cos = rel_err(t.tensor("cos_sim_raw").cpu().numpy().ravel(), c["cos_sim_raw"])
+    print(f"tf32 single-pass {name}: loss rel {e_loss:.2e}, embeddings {e_y:.2e}, cosines {e_cos:.2e}")
+    assert e_loss <= 5e-3 and e_y <= 5e-3 and e_cos <= 5e-3
+    t.backward()
+    g = t.export_grads()
+    g64 = o64.backward(c)
+    for k in ("W1", "W2", "W3"):
+        e = rel_err(g[k], g64[k])
+        print(f"  grad {k}: {e:.2e}")
+        assert e <= 2e-2, k
 
 
 def test_full_size_c2_properties():
@@ -340,7 +410,7 @@ def test_chunked_backward_equals_monolithic():
             t.backward_w1(k, n)
         g = t.export_grads()
         for k in g_ref:
-            assert_close(g[k], g_ref[k], 1e-6, f"chunked grad {k} (n={n})")
+            assert np.array_equal(g[k], g_ref[k]), f"chunked grad {k} (n={n})"
         dp = DataParallelTower(t, n_chunks=n)
         spans = [t.w1_chunk(k, n) for k in range(n)]
         assert spans[0][0] == 0 and sum(c for _, c in spans) == 21128 * 300
@@ -348,8 +418,10 @@ def test_chunked_backward_equals_monolithic():
             t.adam_range(off, cnt, 1.0)
         t.adam_range(dp.w1_end, t.P - dp.w1_end, 1.0)
         t.adam_advance()
-        # same gradients up to the atomic slot order inside dW1's columns; Adam amplifies that (helpers.assert_update_close)
-        assert_update_close(t.export_params(), ref.export_params(), params, conf.use_bn, f"chunked adam (n={n})", l2_tol=1e-3)
+        # the chunked gather sums every column in the same (row) order as the monolithic one: bit-identical parameters
+        pr, pt = ref.export_params(), t.export_params()
+        for k in pr:
+            assert np.array_equal(pr[k], pt[k]), f"chunked adam (n={n}) differs in {k}"
         assert torch.equal(t.beta_pow, ref.beta_pow)
 
 
@@ -399,9 +471,10 @@ def test_embed_docs_feeds_retrieval():
     assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy(), rs)
 
 
-@pytest.mark.parametrize("name", ["C2", "C4", "C4_NOBN"])
+@pytest.mark.parametrize("name", ["C2", "C3", "C4", "C4_NOBN"])
 def test_full_size_baseline_configs_against_oracle(name):
-    """BASELINE.json configs at their full sizes (C2: B=1024, NEG=4; C4: B=1024, NEG=50 with and without BN): one
+    """BASELINE.json configs at their full sizes (C2: B=1024, NEG=4; C3: B=8192 -- the per-GPU batch of the data-parallel
+    config; C4: B=1024, NEG=50 with and without BN): one
     training step against the oracle -- loss and cosines at 1e-5, every gradient at the bounds of grad_tolerances,
     the oracle differentiating with the device's relu active set (helpers.align_relu_masks: the two sets may differ only
     at units within helpers.KINK_TOL of the kink)."""
