@@ -37,6 +37,8 @@ def workload_conf(name: str, gemm_mode: str = "tc_3xtf32"):
 
 
 def describe(conf, name, n_gpus, extra=None):
+    """The `config` object: identical in both arms (--impl ours / reference) for the same workload and N -- everything
+    arm-specific (gemm mode, exchange, graph replay ...) goes into the separate `run` object of our arm."""
     d = {"workload": f"{name}: TRIGRAM_D={conf.TRIGRAM_D}, layers={'-'.join(map(str, conf.layers))}, NEG={conf.NEG}, "
                      f"query_BS={conf.query_BS} per GPU, BN={'on' if conf.use_bn else 'off'}, fwd+bwd+Adam",
          "query_BS_per_gpu": conf.query_BS, "global_query_BS": conf.query_BS * n_gpus, "NEG": conf.NEG,
@@ -99,7 +101,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def threaded_port(ocfg, params, threads: int):
+def threaded_port(ocfg, params, threads: int, dtype=np.float32):
     """The oracle with its three large loops spread over all host threads -- same arithmetic, element for element.
     NumPy ufuncs and SciPy's sparse kernels release the GIL, so X@W1 is split by row blocks, X^T@dh1 by column blocks of
     dh1 and Adam by parameter ranges over a thread pool; the dense layers already use every OpenBLAS thread.  (TensorFlow
@@ -156,7 +158,7 @@ def threaded_port(ocfg, params, threads: int):
             shape = g.shape
             self.p[k], self.m[k], self.v[k] = p.reshape(shape), m.reshape(shape), v.reshape(shape)
 
-    return ThreadedPort(ocfg, params)
+    return ThreadedPort(ocfg, params, dtype)
 
 
 def cpu_port_step_time(conf, batches, params, steps: int, threads: int):
@@ -186,7 +188,8 @@ def host_threads():
 
 def run_reference(args):
     """--impl reference: TensorFlow (the reference's engine) is not installable here, so the reference arm is the
-    CPU restatement of its graph (oracle/, kind 'port') on all host cores.  Rank 0 only."""
+    CPU restatement of its graph (oracle/, kind 'port') on all host cores.  Rank 0 only.  Nothing on this arm maps the
+    product library (dssm_b200's ctypes binding loads lazily, on the first C call; none is made here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -207,12 +210,14 @@ def run_reference(args):
     value = conf.query_BS / (ms / 1e3)
     sample = (f"{args.steps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy port, one process, sparse "
               f"products / Adam / dense layers on {threads} threads")
+    import dssm_b200._lib as _l
+
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": describe(conf, args.workload, 1, {"parallelism": "cpu"}),
+            "dtype": "f32", "data": "synthetic", "config": describe(conf, args.workload, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "product_library_loaded": _l.loaded()}
     print(json.dumps(line))
 
 
@@ -220,73 +225,137 @@ def run_reference(args):
 def algorithmic_bytes(conf, nnz, P):
     """SURVEY.md section 8(d) formulas, with the ACTUAL nnz of the generated batches."""
     R, D, L1 = conf.rows, conf.TRIGRAM_D, conf.layers[0]
+    widths = list(conf.layers)
     return {
         "spmm_fwd": nnz * (4 * L1 + 8) + R * 4 * L1 + (R + 1) * 4,
         "dw_gather": nnz * (4 * L1 + 8) + D * 4 * L1,
         "adam": 28 * P,
+        "dense": R * 4 * sum(widths) * 6,  # c = 6 activation passes
+        "cos_loss": 2 * R * 4 * widths[-1],
     }
 
 
-def run_ours(args):
-    # NCCL prints its version banner on stdout: keep fd 1 clean for the single JSON line
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-    import torch
-    import torch.distributed as dist
+def dense_flops(conf):
+    w = list(conf.layers)
+    return 6.0 * conf.rows * sum(a * b for a, b in zip(w[:-1], w[1:]))
 
+
+def pct(xs, q):
+    return float(np.percentile(np.asarray(xs, dtype=np.float64), q))
+
+
+def epoch_matrices(batches, conf):
+    """The three epoch matrices pull_batch slices (utils/utils.py:45-61), built by stacking the batches' parts."""
+    import scipy.sparse as sp
+
+    B = conf.query_BS
+    Xs = [b.to_scipy() for b in batches]
+    q = sp.vstack([X[:B] for X in Xs], format="csr")
+    p = sp.vstack([X[B:2 * B] for X in Xs], format="csr")
+    n = sp.vstack([X[2 * B:] for X in Xs], format="csr")
+    return q, p, n
+
+
+class Env:
+    """Process-wide bench state: rank / world / device and the collective helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, flag: bool) -> bool:
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1 if flag else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+def build_tower(env, conf, batches, params, dp_comm, sync_bn=False):
+    """(tower, dp or None).  The choice of symmetric memory is made collectively: every rank falls back together."""
     from dssm_b200 import DSSMTower
     from dssm_b200.parallel import DataParallelTower
+
+    max_nnz = max(b.nnz for b in batches)
+    want_symm = env.world > 1 and dp_comm == "nvlink"
+    tower = None
+    if want_symm:
+        try:
+            tower = DSSMTower(conf, max_nnz=max_nnz, device=env.dev, params=params, symmetric=True)
+            ok = True
+        except Exception as e:  # no symmetric-memory allocator on this box / torch build
+            print(f"[bench] rank {env.rank}: symmetric memory unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+            ok = False
+        if not env.all_true(ok):
+            if env.rank == 0:
+                print("[bench] falling back to --dp-comm nccl on ALL ranks", file=sys.stderr)
+            dp_comm, tower = "nccl", None
+    if tower is None:
+        tower = DSSMTower(conf, max_nnz=max_nnz, device=env.dev, params=params)
+    dp = DataParallelTower(tower, comm=dp_comm, sync_bn=sync_bn) if env.world > 1 else None
+    return tower, dp
+
+
+def timed_steps(env, step, steps, warmup, sampler=None):
+    """W warm-up steps, then EXACTLY `steps` steps between barrier + synchronize, one CUDA event after every step on the
+    launch stream: total = first -> last event (max over ranks), plus the per-step distribution of this rank."""
+    torch = env.torch
+    for i in range(warmup):
+        step(i)
+    env.barrier()
+    if sampler is not None:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    env.barrier()
+    evs[0].record(env.stream)
+    for i in range(steps):
+        step(i)
+        evs[i + 1].record(env.stream)
+    env.barrier()
+    ms_total = env.max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return ms_total, per
+
+
+def run_train_workload(env, args, name, steps, warmup, primary):
+    """Device-resident `value` leg and host-fed `e2e` leg of one workload; roofline block when primary."""
+    import torch
+
+    from dssm_b200.loader import HostBatchLoader
     from dssm_b200.synthetic import init_params, make_batch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-    conf = workload_conf(args.workload, args.gemm_mode)
-    NB = 4  # distinct batches cycled through (each rank its own seeds)
+    rank, world = env.rank, env.world
+    conf = workload_conf(name, args.gemm_mode)
+    NB = 4 if conf.rows > 20000 else 8  # distinct batches cycled through (each rank its own seeds)
     batches = [make_batch(conf, seed=1000 * rank + s) for s in range(NB)]
-    max_nnz = max(b.nnz for b in batches)
     mean_nnz = float(np.mean([b.nnz for b in batches]))
     params = init_params(conf, 0)
-    want_symm = world > 1 and args.dp_comm == "nvlink"
-    try:
-        tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params, symmetric=want_symm)
-    except Exception as e:  # no symmetric-memory allocator on this box / torch build: NCCL exchange instead, loudly
-        if not want_symm:
-            raise
-        print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); falling back to --dp-comm nccl", file=sys.stderr)
-        args.dp_comm = "nccl"
-        tower = DSSMTower(conf, max_nnz=max_nnz, device=dev, params=params)
+    tower, dp = build_tower(env, conf, batches, params, args.dp_comm)
     dev_batches = [tower.to_device(b) for b in batches]
-    pinned = [tower.pin(b) for b in batches]
-    dp = DataParallelTower(tower, comm=args.dp_comm) if world > 1 else None
-    stream = torch.cuda.current_stream()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---- leg 1: device-resident inputs ("value") ------------------------------------------------------
     if world == 1:
@@ -299,123 +368,333 @@ def run_ours(args):
         dp.capture_graph()
 
         def step(i):
-            dp.train_step(dev_batches[i % NB])  # stage (D2D) + graph(fwd, dense bwd, CSC) + chunked gather/all-reduce/Adam
+            dp.train_step(dev_batches[i % NB])  # stage (D2D) + one graph: fwd, bwd, CSC, gather, exchange, Adam
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(env.local_rank) if (primary and rank == 0) else None
     launches0 = tower.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total, per = timed_steps(env, step, steps, warmup, sampler)
     launches = tower.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / args.steps
+    clocks = sampler.stop() if sampler is not None else None
+    ms_per_step = ms_total / steps
     value = conf.query_BS * world / (ms_per_step / 1e3)
+    out = {"dp_comm": (dp.comm if dp else None), "dp_mc": (bool(getattr(dp, "use_multicast", False)) if dp else None),
+           "conf": conf, "tower": tower, "dp": dp, "batches": batches, "params": params, "mean_nnz": mean_nnz, "NB": NB,
+           "value": value, "ms_per_step": ms_per_step, "launches": int(launches), "clocks": clocks,
+           "step_ms": {"median": pct(per, 50), "p10": pct(per, 10), "p90": pct(per, 90), "n": len(per),
+                       "note": "per-step CUDA-event intervals of rank 0 inside the timed region"}}
 
-    # ---- leg 2: end to end from HOST buffers through the public API ("e2e") ---------------------------
-    # Double-buffered feed (dssm_tower_train_step_host_async / DataParallelTower.train_step_host_async): every step uploads
-    # ITS OWN CSR from pinned host memory (on the tower's copy stream, overlapping the previous step's kernels), runs the
-    # step (N>1: the data-parallel one, exchange included) and copies its loss back to the host; the host reads each
-    # loss one step late so that it never drains the GPU queue.
+    # ---- leg 2: end to end from HOST data through the public API ("e2e") ------------------------------
+    # The epoch matrices (what the reference's training loop holds: query_train_dat / doc_train_dat / doc_neg_train_dat,
+    # new_dssm.py:37-39) live in host memory; HostBatchLoader's worker thread assembles every step's stacked CSR into a
+    # pinned ring INSIDE the timed region, the tower uploads it on its copy stream under the previous step's kernels
+    # (dssm_tower_train_step_host_async / DataParallelTower.train_step_host_async) and every step's loss is read back by
+    # the host, one step late so that the GPU queue never drains.
+    q, p, n = epoch_matrices(batches, conf)
+    loader = HostBatchLoader(q, p, n, conf.query_BS, conf.NEG, max_nnz=tower.max_nnz)
     step_async = tower.train_step_host_async if world == 1 else dp.train_step_host_async
-    in_flight = [None]
 
-    def e2e_step(i):
-        k = step_async(pinned[i % NB])
-        loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
-        in_flight[0] = k
-        return loss
+    def run_epoch(n_steps):
+        prev, last = None, None
+        for pinned in loader.iterate([i % NB for i in range(n_steps)]):
+            k = step_async(pinned)
+            if prev is not None:
+                last = tower.feed_loss(prev)
+            prev = k
+        if prev is not None:
+            last = tower.feed_loss(prev)  # the last step's loss has landed on the host before the clock stops
+        return last
 
-    def e2e_flush():
-        loss = tower.feed_loss(in_flight[0]) if in_flight[0] is not None else None
-        in_flight[0] = None
-        return loss
-
-    for i in range(max(args.warmup, 1)):
-        e2e_step(i)
-    e2e_flush()
-    barrier()
+    run_epoch(max(warmup, 2))
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record(stream)
-    last_loss = None
-    for i in range(args.steps):
-        last_loss = e2e_step(i)
-    flushed = e2e_flush()  # the last step's loss has landed on the host before the clock stops
-    last_loss = flushed if flushed is not None else last_loss
-    e1.record(stream)
-    barrier()
+    e0.record(env.stream)
+    last_loss = run_epoch(steps)
+    e1.record(env.stream)
+    env.barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
-    e2e_value = conf.query_BS * world / (e2e_ms / 1e3)
-    h2d = int(4 * (conf.rows + 1) + 8 * mean_nnz)
+    e2e_ms = env.max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / steps
+    out["e2e"] = {"value": conf.query_BS * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(4 * (conf.rows + 1) + 8 * mean_nnz),
+                  "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "last_loss": last_loss,
+                  "feed": "HostBatchLoader over host epoch matrices (batch assembly inside the clock) -> pinned ring -> double-buffered upload"}
+    return out
 
-    # ---- roofline: per-phase device time inside real (un-graphed) steps, CUDA events on the launch stream
-    roof = None
-    phases_avg = None
+
+def roofline_block(env, args, res, hbm_peak, peak_src, peaks):
+    """Per-phase device time inside real (un-graphed) steps, CUDA events on the launch stream (dssm_tower_profile_step)."""
+    tower, conf, dev_batches_n = res["tower"], res["conf"], res["NB"]
+    dev_batches = [tower.to_device(b) for b in res["batches"]]
+    acc = {}
+    nprof = 6
+    for i in range(nprof + 2):
+        tower.stage(dev_batches[i % dev_batches_n])
+        ph = tower.profile_step()
+        if i >= 2:
+            for k, v in ph.items():
+                acc[k] = acc.get(k, 0.0) + v / nprof
+    ab = algorithmic_bytes(conf, res["mean_nnz"], tower.P)
+    kern = {k: {"ms": acc[k], "algorithmic_bytes": ab[k], "GBps": ab[k] / (acc[k] * 1e-3) / 1e9,
+                "frac": ab[k] / (acc[k] * 1e-3) / 1e9 / hbm_peak} for k in ("spmm_fwd", "dw_gather", "adam")}
+    dom = "spmm_fwd"  # the kernel north_star puts the >=70 %-of-HBM bar on
+    traffic, l2_bytes = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath)).get(args.workload, {})
+            traffic, l2_bytes = tj.get(dom), tj.get(dom + "_l2_bytes")
+        except Exception:
+            traffic = None
+    dom_s = kern[dom]["ms"] * 1e-3
+    step_bytes = float(sum(ab.values()))
+    step_s = res["ms_per_step"] * 1e-3
+    fl = dense_flops(conf)
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1426.5))
+    dense_ms = acc["dense_fwd"] + acc["dense_bwd"]
+    return {"kernel": "spmm_fwd_v4_kernel (FC1 CSR gather-accumulate)", "bound": "hbm", "achieved": kern[dom]["GBps"],
+            "peak": hbm_peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": kern[dom]["ms"],
+            # the contract `frac` charges one W1 row per non-zero (SURVEY 8d); Zipf-hot rows and the 59 MB W1 live in L1/L2, so it
+            # can exceed 1.  What the kernel really pulls from DRAM / L2 (ncu capture, per launch) over the live launch time:
+            "dram_frac": (traffic / dom_s / 1e9 / hbm_peak) if traffic else None,
+            "l2_frac_of_algorithmic": (l2_bytes / ab[dom]) if l2_bytes else None,
+            "reading": "frac = SURVEY 8(d) algorithmic bytes / live launch time / HBM peak (a gather figure: > 1 means cache hits); "
+                       "dram_frac = ncu dram bytes per launch / live launch time / HBM peak; the whole-step figure is in `step`",
+            "step": {"algorithmic_bytes": step_bytes, "ms": res["ms_per_step"], "GBps": step_bytes / step_s / 1e9,
+                     "frac": step_bytes / step_s / 1e9 / hbm_peak,
+                     "roofline_ms": step_bytes / (hbm_peak * 1e9) * 1e3,
+                     "terms": {k: float(v) for k, v in ab.items()}},
+            "dense": {"flops_useful": fl, "ms_in_profiled_step": dense_ms, "TFLOPs_useful": fl / (dense_ms * 1e-3) / 1e12,
+                      "tensor_issue_factor": 3 if conf.gemm_mode == "tc_3xtf32" else 1,
+                      "frac_of_bf16_sustained_peak": fl / (dense_ms * 1e-3) / 1e12 / tf_peak,
+                      "note": "dense_fwd + dense_bwd phases include the BN kernels; per-kernel tensor-pipe % is in profiles/ (ncu)"},
+            "other_kernels": {k: v for k, v in kern.items() if k != dom},
+            "phase_ms": acc, "phase_share_of_step": {k: v / sum(acc.values()) for k, v in acc.items()}}
+
+
+def dp_parity(env, args, res, sync_bn=False, multicast=None):
+    """Correctness evidence at N>1 where the driver can see it: restore known parameters, run ONE data-parallel step of the
+    benchmarked workload and compare, on rank 0, against the oracle (DPOracle semantics: per-replica BN moments, mean
+    gradient, one TF-Adam step; with sync_bn: the single-process reference on the re-stacked global batch); all ranks
+    check that every replica's parameters are BIT-identical after the exchange."""
+    import torch
+    import torch.distributed as dist
+
+    from dssm_b200.parallel import DataParallelTower
+    from dssm_b200.synthetic import make_batch
+    from oracle import DSSMOracle, OracleConfig
+
+    tower, conf, params = res["tower"], res["conf"], res["params"]
+    rank, world = env.rank, env.world
+    t_start = time.perf_counter()
+    dp = DataParallelTower(tower, comm=args.dp_comm if res["dp"].comm == "nvlink" else "nccl", sync_bn=sync_bn, multicast=multicast)
+    if not sync_bn and tower.conf.use_bn:
+        from dssm_b200._lib import check, lib
+
+        check(lib.dssm_tower_set_syncbn(tower._h, 1, 0, None))
+    # known state: initial parameters, zero optimizer state and shadows
+    tower.load_params(params)
+    tower.m.zero_(); tower.v.zero_(); tower.comm.zero_()
+    tower.beta_pow.copy_(torch.tensor([conf.beta1, conf.beta2], dtype=torch.float32))
+    b = make_batch(conf, seed=7000 + rank)
+    loss_local = dp.train_step(tower.to_device(b)).item()
+    torch.cuda.synchronize()
+    # replicas bit-identical?
+    ref = tower.params.clone()
+    dist.broadcast(ref, src=0)
+    identical = env.all_true(bool(torch.equal(ref, tower.params)))
+    out = {"sync_bn": sync_bn, "comm": dp.comm, "nvls_multicast": bool(getattr(dp, "use_multicast", False)),
+           "replicas_bit_identical": identical}
+    losses = [torch.zeros(1, dtype=torch.float64, device=env.dev) for _ in range(world)]
+    dist.all_gather(losses, torch.tensor([loss_local], dtype=torch.float64, device=env.dev))
     if rank == 0:
-        acc = {}
-        nprof = max(3, min(args.steps, 10))
-        for i in range(nprof + 2):
-            tower.stage(dev_batches[i % NB])
-            ph = tower.profile_step()
-            if i >= 2:
-                for k, v in ph.items():
-                    acc[k] = acc.get(k, 0.0) + v / nprof
-        phases_avg = acc
-        ab = algorithmic_bytes(conf, mean_nnz, tower.P)
-        kern = {k: {"ms": acc[k], "algorithmic_bytes": ab[k], "GBps": ab[k] / (acc[k] * 1e-3) / 1e9,
-                    "frac": ab[k] / (acc[k] * 1e-3) / 1e9 / hbm_peak} for k in ab}
-        dom = "spmm_fwd"  # the kernel north_star puts the >=70 %-of-HBM bar on
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
-            except Exception:
-                traffic = None
-        roof = {"kernel": "spmm_fwd_v4_kernel (FC1 CSR gather-accumulate)", "bound": "hbm", "achieved": kern[dom]["GBps"],
-                "peak": hbm_peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": kern[dom]["ms"],
-                "other_kernels": {k: v for k, v in kern.items() if k != dom},
-                "phase_ms": acc, "phase_share_of_step": {k: v / sum(acc.values()) for k, v in acc.items()}}
+        from threadpoolctl import threadpool_limits
+
+        threads = host_threads()
+        mats = [make_batch(conf, seed=7000 + r).to_scipy() for r in range(world)]
+
+        def ocfg(B):
+            return OracleConfig(TRIGRAM_D=conf.TRIGRAM_D, layers=tuple(conf.layers), NEG=conf.NEG, query_BS=B,
+                                learning_rate=conf.learning_rate, use_bn=conf.use_bn, act=conf.act, loss_eps=conf.loss_eps,
+                                loss_div_bs=conf.loss_div_bs)
+
+        with threadpool_limits(limits=threads):
+            if sync_bn:
+                from oracle.syncbn import restack_global
+
+                X = restack_global(mats, conf.query_BS, conf.NEG)
+                o64 = threaded_port(ocfg(conf.query_BS * world), params, threads, np.float64)
+                o32 = threaded_port(ocfg(conf.query_BS * world), params, threads)
+                c64, c32 = o64.forward(X, on_train=True), o32.forward(X, on_train=True)
+                g64, g32 = o64.backward(c64), o32.backward(c32)
+                ref_loss = float(c64["loss"])
+                got_loss = float(np.mean([l.item() for l in losses]))  # mean of the local losses = global-batch loss
+                o32.adam_update(g32)
+                ref_params = o32.p
+            else:
+                o64 = threaded_port(ocfg(conf.query_BS), params, threads, np.float64)
+                o32 = threaded_port(ocfg(conf.query_BS), params, threads)
+                g64 = g32 = None
+                ref_loss = None
+                for r, X in enumerate(mats):
+                    c64, c32 = o64.forward(X, on_train=True, update_ema=False), o32.forward(X, on_train=True, update_ema=False)
+                    a, b32 = o64.backward(c64), o32.backward(c32)
+                    if r == 0:
+                        ref_loss = float(c64["loss"])
+                    g64 = a if g64 is None else {k: g64[k] + a[k] for k in a}
+                    g32 = b32 if g32 is None else {k: g32[k] + b32[k] for k in b32}
+                g64 = {k: v / world for k, v in g64.items()}
+                g32 = {k: (v / np.float32(world)).astype(np.float32) for k, v in g32.items()}
+                got_loss = losses[0].item()
+                o32.adam_update(g32)
+                ref_params = o32.p
+        loss_rel = abs(got_loss - ref_loss) / abs(ref_loss)
+        got_g = tower.export_grads()
+        worst, bad = 0.0, []
+        for k, r64 in g64.items():
+            if k == "W1" and dp.comm == "nvlink":
+                continue  # the dense dW1 stays LOCAL under the fused exchange (only the owner ever sees the mean)
+            if conf.use_bn and k[0] == "b" and k[1:].isdigit():
+                continue  # analytically zero under BN: rounding noise on both sides
+            scale = max(float(np.abs(r64).max()), 1e-30)
+            allow = max(5e-5 * scale, 4 * float(np.abs(g32[k].astype(np.float64) - r64).max()))
+            err = float(np.abs(got_g[k].astype(np.float64) - r64).max())
+            worst = max(worst, err / scale)
+            if err > allow:
+                bad.append(k)
+        got_p = tower.export_params()
+        num = den = 0.0
+        for k in ("W1", "W2", "W3"):
+            if k in got_p:
+                num += float(np.linalg.norm((got_p[k].astype(np.float64) - ref_params[k]).ravel()) ** 2)
+                den += float(np.linalg.norm((ref_params[k].astype(np.float64) - params[k]).ravel()) ** 2)
+        upd_rel = (num / max(den, 1e-300)) ** 0.5
+        out.update({"loss_rel_err": loss_rel, "grad_max_rel_err": worst, "grads_outside_bounds": bad,
+                    "param_update_rel_l2": upd_rel,
+                    "bounds": "loss 1e-5; gradients max(5e-5 x scale, 4 x the fp32 port's own error vs float64); update rel-L2 0.1 "
+                              "(first Adam step is lr*sign(g): near-zero gradients flip)",
+                    "oracle_s": time.perf_counter() - t_start})
+        out["ok"] = bool(identical and loss_rel <= 1e-5 and not bad and upd_rel <= 0.1)
+    dist.barrier()
+    return out
+
+
+def retrieval_block(env, args, peaks):
+    """Corpus cosine top-k (BASELINE.json C5: 10 M x 128 docs over 8 GPUs, 4096 queries, top-100): every rank scores its
+    1.25 M-doc shard (tcgen05 filter + exact rescoring), the (score, id) lists are all-gathered and merged on every rank.
+    docs/s = corpus docs scored for the whole query batch per second (all ranks).  N>1: ids checked against the exact
+    SIMT path on a query sub-sample over the same sharded corpus."""
+    import torch
+    import torch.distributed as dist
+
+    from dssm_b200 import retrieval as rt
+
+    dev, world, rank = env.dev, env.world, env.rank
+    nqr, ndr, kr = 4096, 1_250_000, 100
+    g = torch.Generator(device=dev).manual_seed(0)
+    Qr = torch.relu(torch.randn((nqr, 128), generator=g, device=dev))  # same queries on every rank
+    gd = torch.Generator(device=dev).manual_seed(100 + rank)
+    Dr = torch.relu(torch.randn((ndr, 128), generator=gd, device=dev))  # this rank's shard
+    total = ndr * world
+
+    def once(Q, method="tc"):
+        if world == 1:
+            return rt.corpus_topk(Q, Dr, kr, method=method)
+        return rt.sharded_corpus_topk(Q, Dr, kr, id_offset=rank * ndr, total_docs=total, method=method)
+
+    once(Qr)  # warm-up (attribute calls, allocator, NCCL channels)
+    env.barrier()
+    reps = 3
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(env.stream)
+    for _ in range(reps):
+        rs_, ri_ = once(Qr)
+    r1.record(env.stream)
+    env.barrier()
+    rms = env.max_over_ranks(r0.elapsed_time(r1)) / reps
+    fell_back = bool(rt.LAST_CALL["fallback"])
+    check = None
+    if world > 1:
+        sub = 64
+        es, ei = once(Qr[:sub].contiguous(), method="exact")
+        same = bool(torch.equal(ei, ri_[:sub]) and torch.equal(es, rs_[:sub]))
+        check = {"queries_checked": sub, "ids_and_scores_equal_exact_path": env.all_true(same)}
+    flops = 2.0 * nqr * total * 128
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1426.5))
+    return {"metric": "corpus cos top-k docs/s", "value": total / (rms / 1e3), "unit": "docs/s", "ms": rms, "n_gpus": world,
+            "config": {"queries": nqr, "docs_total": total, "docs_per_gpu": ndr, "dim": 128, "k": kr, "storage": "fp32",
+                       "method": "tcgen05 tf32 filter + exact fp32 rescoring (ids bit-exact vs oracle); N>1: NCCL all-gather of the "
+                                 "per-shard lists + merge kernel on every rank"},
+            "fallback_to_exact": fell_back, "tf32_tflops": flops / (rms / 1e3) / 1e12,
+            "frac_of_tensor_ceiling": (total / (rms / 1e3)) / (world * tf_peak * 1e12 / (2.0 * nqr * 128)),
+            "sharded_check": check,
+            "includes": "row norms, exact seed pass, filter passes, rescoring, overflow-flag readback" +
+                        (", all-gather, merge" if world > 1 else "")}
+
+
+def run_ours(args):
+    # NCCL prints its version banner on stdout: keep fd 1 clean for the single JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    env = Env(args)
+    import torch
+    import torch.distributed as dist
+
+    rank, world = env.rank, env.world
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    res = run_train_workload(env, args, args.workload, args.steps, args.warmup, primary=True)
+    conf, tower, dp = res["conf"], res["tower"], res["dp"]
+    roof = roofline_block(env, args, res, hbm_peak, peak_src, peaks) if rank == 0 and world == 1 else None
     if world > 1:
         dist.barrier()
 
-    # ---- secondary metric: corpus cosine top-k (BASELINE.json C5, one GPU's shard) ----------------------------
-    retrieval = None
-    if rank == 0 and world == 1 and not args.no_retrieval:
-        from dssm_b200 import retrieval as rt
+    # ---- correctness evidence for the multi-GPU paths (N>1) -----------------------------------------------------
+    parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp.graph = None
+        parity = {"default": dp_parity(env, args, res)}
+        if dp.comm == "nvlink":
+            other = not bool(getattr(dp, "use_multicast", False))
+            parity["nvls_multicast" if other else "peer_loads_stores"] = dp_parity(env, args, res, multicast=other)
+        if conf.use_bn:
+            parity["sync_bn"] = dp_parity(env, args, res, sync_bn=True)
+        if rank == 0:
+            parity["ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict))
 
-        g = torch.Generator(device=dev).manual_seed(0)
-        nqr, ndr, kr = 4096, 1_250_000, 100  # 10 M docs / 8 GPUs, query batch 4096, top-100
-        Qr = torch.relu(torch.randn((nqr, 128), generator=g, device=dev))
-        Dr = torch.relu(torch.randn((ndr, 128), generator=g, device=dev))
-        rt.corpus_topk(Qr, Dr, kr, method="tc")  # warm-up (attribute calls, allocator)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        r0.record(stream)
-        for _ in range(reps):
-            rs_, ri_ = rt.corpus_topk(Qr, Dr, kr, method="tc")
-        r1.record(stream)
-        torch.cuda.synchronize()
-        rms = r0.elapsed_time(r1) / reps
-        flops = 2.0 * nqr * ndr * 128
-        retrieval = {"metric": "corpus cos top-k docs/s", "value": ndr / (rms / 1e3), "unit": "docs/s", "ms": rms,
-                     "config": {"queries": nqr, "docs_per_gpu": ndr, "dim": 128, "k": kr, "storage": "fp32",
-                                "method": "tcgen05 tf32 filter + exact fp32 rescoring (ids bit-exact vs oracle)"},
-                     "fallback_to_exact": bool(rt.LAST_CALL["fallback"]), "tf32_tflops": flops / (rms / 1e3) / 1e12,
-                     "includes": "row norms, exact seed pass (16384 docs), 3 filter passes, rescoring, overflow-flag readback"}
-        del Qr, Dr
+    # ---- single-pass tf32 dense mode (stated tolerance: include/dssm_b200.h) --------------------------------------
+    tf32 = None
+    if world == 1 and not args.no_extras and args.gemm_mode == "tc_3xtf32":
+        a2 = argparse.Namespace(**vars(args))
+        a2.gemm_mode = "tc_tf32"
+        r2 = run_train_workload(env, a2, args.workload, min(args.steps, 20), 3, primary=False)
+        tf32 = {"gemm_mode": "tc_tf32", "value": r2["value"], "ms_per_step": r2["ms_per_step"],
+                "tolerance": "loss / embeddings / cosines within 5e-3 of scale vs the float64 oracle (tests/test_gpu_tower.py::test_tf32_mode_tolerance)"}
+        del r2
+
+    # ---- BASELINE configs[2]: C3 = 8192 groups per GPU, at every N --------------------------------------------------
+    c3 = None
+    if not args.no_extras and args.workload.upper() != "C3":
+        res["tower"] = res["dp"] = tower = dp = None
+        torch.cuda.empty_cache()
+        r3 = run_train_workload(env, args, "C3", min(args.steps, 10), 3, primary=False)
+        c3 = {"workload": describe(r3["conf"], "C3", world)["workload"], "value": r3["value"], "unit": UNIT, "n_gpus": world,
+              "ms_per_step": r3["ms_per_step"], "steps": min(args.steps, 10), "step_ms": r3["step_ms"], "e2e": r3["e2e"],
+              "dp_comm": (r3["dp"].comm if r3["dp"] else None),
+              "dp_nvls_multicast": (getattr(r3["dp"], "use_multicast", None) if r3["dp"] else None)}
+        if r3["dp"] is not None:
+            r3["dp"].graph = None
+        del r3
+        torch.cuda.empty_cache()
+
+    # ---- secondary metric: corpus cosine top-k (BASELINE.json C5) -----------------------------------------------------
+    retrieval = None
+    if not args.no_retrieval:
+        retrieval = retrieval_block(env, args, peaks)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores -----------------------------
     cpu = None
@@ -425,31 +704,30 @@ def run_ours(args):
         from threadpoolctl import threadpool_limits
 
         with threadpool_limits(limits=threads):
-            times = cpu_port_step_time(conf, batches[:2], params, nsteps, threads)
+            times = cpu_port_step_time(conf, res["batches"][:2], res["params"], nsteps, threads)
         cpu = {"value": conf.query_BS / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{nsteps} full {args.workload} train steps (query_BS={conf.query_BS}) of the NumPy/SciPy oracle "
                          f"(sparse products, Adam and dense layers on all {threads} host threads)",
                "ms_per_step": 1e3 * float(np.mean(times))}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": describe(conf, args.workload, world, {"mean_nnz_per_step_per_gpu": mean_nnz, "gemm_mode": conf.gemm_mode,
-                                                               "distinct_batches": NB, "cuda_graph": True,
-                                                               "dp_w1_chunks": (dp.n_chunks if dp else None),
-                                                               "dp_comm": (dp.comm if dp else None),
-                                                               "dp_nvls_multicast": (getattr(dp, "use_multicast", None) if dp else None)}),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": e2e_ms, "last_loss": last_loss},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "retrieval": retrieval}
+                "config": describe(conf, args.workload, world),
+                "run": {"mean_nnz_per_step_per_gpu": res["mean_nnz"], "gemm_mode": conf.gemm_mode, "distinct_batches": res["NB"],
+                        "cuda_graph": True, "dp_comm": res["dp_comm"], "dp_nvls_multicast": res["dp_mc"],
+                        "bn_moments": "per-replica (the SyncBN option is exercised in dp_parity)" if world > 1 else "batch",
+                        "deterministic": "bit-reproducible step (row-ordered CSC columns, fixed-order merges)" +
+                                         ("; NVLS multimem.ld_reduce order is the switch's" if res["dp_mc"] else "")},
+                "step_ms": res["step_ms"], "e2e": res["e2e"], "gpu_launches": res["launches"], "clocks": res["clocks"],
+                "roofline": roof, "cpu_baseline": cpu, "dp_parity": parity, "tf32_single_pass": tf32, "c3": c3, "retrieval": retrieval}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Tear-down: a process group that has collectives captured in a live CUDA graph can block forever in
         # destroy_process_group (seen on NCCL 2.28.9: the JSON line was out, the ranks never exited).  Drop the
         # graph first, meet at a barrier, and leave without the NCCL destructor if it does not return promptly.
         torch.cuda.synchronize()
-        dp.graph = None
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
@@ -470,11 +748,13 @@ def main():
     ap.add_argument("--workload", default="C2", help="C1 | C2 | C3 | C4 | C4_NOBN (per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the secondary corpus top-k measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 block and the single-pass tf32 leg")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the oracle check of one data-parallel step")
     ap.add_argument("--dp-comm", default="nvlink", choices=["nccl", "nvlink"],
                     help="N>1: dW1 exchange by NCCL all-reduce (chunked, overlapped) or by the fused pull/Adam/push kernel over "
                          "NVLink peer memory (csrc/nvlink.cu)")
-    ap.add_argument("--gemm-mode", default="tc_3xtf32", choices=["fp32", "tc_3xtf32"],
-                    help="dense-layer arithmetic: FFMA fp32 or tcgen05 3xTF32 (both hold the 1e-5 parity bar)")
+    ap.add_argument("--gemm-mode", default="tc_3xtf32", choices=["fp32", "tc_3xtf32", "tc_tf32"],
+                    help="dense-layer arithmetic: FFMA fp32 or tcgen05 3xTF32 (both hold the 1e-5 parity bar), or single-pass tf32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

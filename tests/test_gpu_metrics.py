@@ -65,7 +65,7 @@ def test_eval_step_is_one_forward_and_matches_three_reference_runs():
         u.run("Auc/auc/update_op:0", feed)
         auc_v = u.run("Auc/auc/value:0", feed)
         assert u.launch_count - n1 == 3 * fwd_launches
-        assert loss.item() == float(loss_v)
+        assert loss.item() == float(np.asarray(loss_v).reshape(-1)[0])
         want = host.update(labels_for(B, conf.NEG), t.tensor("cos_sim_raw").cpu().numpy())
         assert abs(a.item() - want) <= 1e-12 and abs(float(auc_v) - want) <= 1e-6
     acc = t.tensor("accuracy").item()
