@@ -126,6 +126,7 @@ SIGNATURES = {
     "dssm_tower_feed_wait": (C.c_int, [_p, _i64]),
     "dssm_tower_feed_upload_async": (C.c_int64, [_p, _p, _p, _p, _i64, _p]),
     "dssm_tower_feed_step_done": (C.c_int, [_p, _i64, _p, _p]),
+    "dssm_host_stack_csr": (_i64, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32]),
     "dssm_tower_launch_count": (_i64, [_p]),
     "dssm_tower_profile_step": (C.c_int, [_p, C.POINTER(C.c_float), _p]),
     "dssm_tower_profile_step_overlapped": (C.c_int, [_p, C.POINTER(C.c_float), _p]),

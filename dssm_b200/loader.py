@@ -66,7 +66,7 @@ class HostBatchLoader:
     batch ids of `new_dssm.py:262-265`."""
 
     def __init__(self, query_data, doc_data, doc_neg_data, query_BS: int, NEG: int, max_nnz: Optional[int] = None,
-                 depth: int = 5, pin: Optional[bool] = None):
+                 depth: int = 5, pin: Optional[bool] = None, native: bool = True, copy_threads: int = 4):
         if depth < 4:
             raise ValueError("depth must be at least 4 (one batch of look-ahead)")
         self.q = _canonical(query_data)
@@ -74,6 +74,7 @@ class HostBatchLoader:
         self.n = _canonical(doc_neg_data, self.q.shape[1])
         if self.p.shape[0] != self.q.shape[0] or self.n.shape[0] != self.q.shape[0] * NEG:
             raise ValueError("need one positive and NEG negatives per query (utils/utils.py:49-51)")
+        self.native, self.copy_threads, self._tab = bool(native), int(copy_threads), None  # assembly by dssm_host_stack_csr (C, GIL-free)
         self.B, self.NEG, self.depth = int(query_BS), int(NEG), int(depth)
         self.R = (2 + self.NEG) * self.B
         self.steps = reference_epoch_steps(self.q.shape[0], self.B)
@@ -102,8 +103,43 @@ class HostBatchLoader:
         """Largest stacked batch of the epoch (size DSSMTower's max_nnz with it)."""
         return max((self.batch_nnz(b) for b in range(max(self.steps, 1)) if (b + 1) * self.B <= self.q.shape[0]), default=0)
 
+    _IK = {np.dtype(np.int32): 0, np.dtype(np.int64): 1}
+    _VK = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int64): 2, np.dtype(np.int32): 3}
+
+    def _native_tables(self):
+        """ctypes tables of the three epoch matrices for dssm_host_stack_csr (built once)."""
+        import ctypes as C
+
+        mats = (self.q, self.p, self.n)
+        for m in mats:
+            if m.indptr.dtype != m.indices.dtype or m.indptr.dtype not in self._IK or m.data.dtype not in self._VK:
+                return None
+        arr = C.c_void_p * 3
+        return dict(ip=arr(*[m.indptr.ctypes.data for m in mats]), ix=arr(*[m.indices.ctypes.data for m in mats]),
+                    vl=arr(*[m.data.ctypes.data for m in mats]),
+                    ik=(C.c_int32 * 3)(*[self._IK[m.indptr.dtype] for m in mats]),
+                    vk=(C.c_int32 * 3)(*[self._VK[m.data.dtype] for m in mats]))
+
     def _fill(self, slot: int, b: int):
         ip, ix, vl = self._bufs[slot]
+        if self.native:
+            import ctypes as C
+
+            from ._lib import DssmError, last_error, lib
+
+            if self._tab is None:
+                self._tab = self._native_tables() or False
+            if self._tab:
+                t = self._tab
+                parts = self._parts(b)
+                lo = (C.c_int64 * 3)(*[p_[1] for p_ in parts])
+                hi = (C.c_int64 * 3)(*[p_[2] for p_ in parts])
+                # one C call (the GIL is released for its duration): three contiguous copies + the offset indptr
+                nnz = lib.dssm_host_stack_csr(3, t["ip"], t["ix"], t["vl"], t["ik"], t["vk"], lo, hi, ip.data_ptr(), ix.data_ptr(),
+                                              vl.data_ptr(), ix.shape[0], self.copy_threads)
+                if nnz < 0:
+                    raise DssmError(int(nnz), last_error())
+                return ip, ix, vl, int(nnz)
         nnz = fill_stacked(self._parts(b), ip.numpy(), ix.numpy(), vl.numpy())
         return ip, ix, vl, nnz
 

@@ -73,6 +73,8 @@ class DataParallelTower:
         self.pipelined = tower.conf.layers[0] % 4 == 0 and off == 0
         self.graph = None
         self.graphed = False
+        self.launches_per_step = 0
+        self.replays = 0
         self.sync_bn = False
         # identical starting state on every rank: parameters AND optimizer state (Adam m, v, beta powers) AND the EMA
         # shadows -- rank 0 may have restored a checkpoint; replicas whose slots differ would apply different updates to
@@ -258,7 +260,9 @@ class DataParallelTower:
             s.wait_stream(torch.cuda.current_stream(t.device))
             with torch.cuda.stream(s):
                 for _ in range(warmup):  # communicators, attribute calls, allocator warm-up outside the capture
+                    n0 = t.launch_count
                     self._step_staged()
+                    self.launches_per_step = t.launch_count - n0  # kernels of OUR library in one step (replays are not counted by the C side)
             torch.cuda.current_stream(t.device).wait_stream(s)
             torch.cuda.synchronize(t.device)
             g = torch.cuda.CUDAGraph()
@@ -289,6 +293,7 @@ class DataParallelTower:
             t.stage(x)
         if self.graph is not None:
             self.graph.replay()
+            self.replays += 1
         else:
             self._step_staged()
         return t.tensor("loss")

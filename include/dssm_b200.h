@@ -376,6 +376,16 @@ int dssm_tower_feed_wait(dssm_tower* t, int64_t step);
 int64_t dssm_tower_feed_upload_async(dssm_tower* t, const int32_t* host_indptr, const int32_t* host_indices,
                                      const float* host_values, int64_t nnz, dssm_stream_t stream);
 int dssm_tower_feed_step_done(dssm_tower* t, int64_t step, float* host_loss, dssm_stream_t stream);
+/* HOST helper of the pipelined feed (no device work): write the rows [row_lo[p], row_hi[p]) of n_parts host CSR matrices,
+ * stacked in order, as ONE int32/fp32 CSR into out_* (typically pinned) -- what pull_batch's three row slices + feed
+ * conversion produce (utils/utils.py:45-61,20-24) without intermediate objects.  index_kind[p]: 0 = int32, 1 = int64
+ * (indptr and indices of part p); value_kind[p]: 0 = float32, 1 = float64, 2 = int64, 3 = int32 (cast to float32 like the
+ * feed does).  out_indptr needs sum(row_hi - row_lo) + 1 entries, out_indices / out_values `capacity`.  Copies are split
+ * over up to n_threads host threads.  Returns nnz, or -1 (dssm_last_error). */
+int64_t dssm_host_stack_csr(int32_t n_parts, const void* const* part_indptr, const void* const* part_indices,
+                            const void* const* part_values, const int32_t* index_kind, const int32_t* value_kind,
+                            const int64_t* row_lo, const int64_t* row_hi, int32_t* out_indptr, int32_t* out_indices,
+                            float* out_values, int64_t capacity, int32_t n_threads);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t dssm_tower_launch_count(const dssm_tower* t);
 /* One un-graphed train step on the staging CSR with CUDA events between the phases; synchronises.

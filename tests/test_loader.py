@@ -97,3 +97,29 @@ def test_fill_stacked_equals_vstack_on_ragged_inputs():
         assert np.array_equal(ix[:nnz], ref.indices) and np.array_equal(vl[:nnz], ref.data.astype(np.float32))
 
     check()
+
+
+def test_native_assembly_equals_python_assembly_for_every_value_type():
+    """dssm_host_stack_csr (C, one call per batch, GIL released) writes the same stacked CSR as the NumPy path, for the
+    value types the reference feeds: int64 counts (CountVectorizer), float64 tf-idf (dssm_tf_idf.py:37), float32
+    (data_input.py:157-159); and refuses a batch larger than the buffers."""
+    import scipy.sparse as sp
+
+    from dssm_b200._lib import DssmError
+    from dssm_b200.loader import HostBatchLoader
+    from tests.helpers import random_csr
+
+    rng = np.random.default_rng(3)
+    B, NEG, nb, D = 16, 3, 5, 300
+    base = [random_csr(rng, B * nb, D), random_csr(rng, B * nb, D), random_csr(rng, B * nb * NEG, D)]
+    for dt in (np.int64, np.float64, np.float32):
+        mats = [sp.csr_matrix(m, dtype=dt) for m in base]
+        a = HostBatchLoader(*mats, B, NEG, pin=False, native=True, copy_threads=3)
+        b = HostBatchLoader(*mats, B, NEG, pin=False, native=False)
+        for (ip1, ix1, vl1, n1), (ip2, ix2, vl2, n2) in zip(a, b):
+            assert n1 == n2
+            assert np.array_equal(ip1.numpy(), ip2.numpy())
+            assert np.array_equal(ix1.numpy()[:n1], ix2.numpy()[:n2]) and np.array_equal(vl1.numpy()[:n1], vl2.numpy()[:n2])
+    small = HostBatchLoader(*base, B, NEG, pin=False, max_nnz=5)
+    with pytest.raises(DssmError):
+        list(small)
