@@ -569,9 +569,23 @@ make_b_image_kernel(const float* __restrict__ src, int N, int K, int ld, int tra
     }
 }
 
-static int pick_bn(int N) {
-    // N tiles of equal width, multiple of 32 (epilogue chunks), at most MAX_BN
-    const int tiles = (N + MAX_BN - 1) / MAX_BN;
+// Width of the N tiles for an [M, N] output.  With many M tiles (C3: 384) the widest tile (160 columns, two tiles for
+// N = 300) keeps the per-CTA fixed costs low.  With few M tiles (C2: 48) the GEMMs are latency-bound with most SMs idle:
+// narrower tiles put more CTAs on the chip (N = 300 -> 3 x 128 -> 144 CTAs on 148 SMs; N = 128 -> 2 x 64 -> 96) and leave
+// ~34 KB of every SM's shared memory to the side-stream kernels that run beside them (160-wide tiles leave 10 KB, which
+// kept CSC-build blocks and GEMM CTAs off each other's SMs).  M <= 0 selects the wide policy.
+static int pick_bn(int N, int M) {
+    const int wide_tiles = (N + MAX_BN - 1) / MAX_BN;
+    int tiles = wide_tiles;
+    if (M > 0) {
+        const int m_tiles = (M + BM - 1) / BM;
+        const int nsm = sm_count();
+        for (int t = wide_tiles + 1; t <= 8; ++t) {
+            const int bn = ((N + t - 1) / t + 31) / 32 * 32;
+            if (bn < 64 || m_tiles * t > nsm || bn * (t - 1) >= N) break;
+            tiles = t;
+        }
+    }
     int bn = ((N + tiles - 1) / tiles + 31) / 32 * 32;
     return bn > MAX_BN ? MAX_BN : bn;
 }
@@ -618,19 +632,21 @@ static int pick_splits_tc(int R, int tiles) {
 using namespace dssm;
 
 // image of an operand with N rows (tiled by BN) and K reduction columns
-static size_t image_bytes(int N, int K) {
-    const int bn = tc::pick_bn(N);
+static size_t image_bytes(int N, int K, int M) {
+    const int bn = tc::pick_bn(N, M);
     return align_up((size_t)cdiv(N, bn) * cdiv(K, tc::BK) * 2 * bn * tc::BK * 4, 256);
 }
 
 extern "C" size_t dssm_fc_tc_workspace_bytes(int32_t K, int32_t N) {
     if (K <= 0 || N <= 0) return 0;
-    const size_t f = image_bytes(N, K), b = image_bytes(K, N);  // forward (B = W^T) and dX (B = W)
+    // forward (B = W^T) and dX (B = W), for any row count (the tile width depends on it): generous bound on the padding
+    const size_t f = align_up((size_t)cdiv(K, tc::BK) * 2 * (size_t)(N + 2 * tc::MAX_BN) * tc::BK * 4, 256);
+    const size_t b = align_up((size_t)cdiv(N, tc::BK) * 2 * (size_t)(K + 2 * tc::MAX_BN) * tc::BK * 4, 256);
     return f > b ? f : b;
 }
 
-static int build_image(const float* src, int N, int K, int ld, int transposed, char* img, cudaStream_t st) {
-    const int bn = tc::pick_bn(N), nkb = cdiv(K, tc::BK);
+static int build_image(const float* src, int N, int K, int ld, int transposed, int M, char* img, cudaStream_t st) {
+    const int bn = tc::pick_bn(N, M), nkb = cdiv(K, tc::BK);
     dim3 grid(cdiv(N, bn), nkb);
     tc::make_b_image_kernel<<<grid, 256, 0, st>>>(src, N, K, ld, transposed, bn, nkb, img);
     LAUNCH_CHECK("make_b_image");
@@ -639,19 +655,22 @@ static int build_image(const float* src, int N, int K, int ld, int transposed, c
 
 // image of W for the forward (transposed = 1: B = W^T) or for dX (transposed = 0: B = W); internal, used by the tower to
 // build all images of a step beside the forward
-extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx) { return for_dx ? image_bytes(K, N) : image_bytes(N, K); }
-extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, void* img, dssm_stream_t stream) {
-    return for_dx ? build_image(W, K, N, N, 0, (char*)img, (cudaStream_t)stream) : build_image(W, N, K, N, 1, (char*)img, (cudaStream_t)stream);
+// R = rows of the activation operand the image will be multiplied with (decides the tile width, pick_bn)
+extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx, int32_t R) {
+    return for_dx ? image_bytes(K, N, R) : image_bytes(N, K, R);
+}
+extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, int32_t R, void* img, dssm_stream_t stream) {
+    return for_dx ? build_image(W, K, N, N, 0, R, (char*)img, (cudaStream_t)stream) : build_image(W, N, K, N, 1, R, (char*)img, (cudaStream_t)stream);
 }
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                                   int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes,
                                   dssm_stream_t stream) {
-    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)img, passes};
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N, R), 0, (const char*)img, passes};
     return tc::launch(a, (cudaStream_t)stream);
 }
 extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes,
                                      dssm_stream_t stream) {
-    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)img, passes};
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K, R), 0, (const char*)img, passes};
     return tc::launch(a, (cudaStream_t)stream);
 }
 
@@ -662,12 +681,12 @@ extern "C" int dssm_fc_fwd_tc(const float* Hprev, int32_t R, int32_t K, int32_t 
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(Hprev) && aligned16(W) && aligned16(Hout) && (!bias || aligned16(bias)) && (!scale || (aligned16(scale) && aligned16(shift))),
                  DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
-    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
+    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(N, K, R) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
                  "dssm_fc_fwd (tc): workspace too small or unaligned");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = build_image(W, N, K, N, 1, (char*)workspace, st);  // B[n][k] = W[k][n]
+    int rc = build_image(W, N, K, N, 1, R, (char*)workspace, st);  // B[n][k] = W[k][n]
     if (rc != DSSM_OK) return rc;
-    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N), 0, (const char*)workspace, passes};
+    tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N, R), 0, (const char*)workspace, passes};
     return tc::launch(a, st);
 }
 
@@ -676,13 +695,13 @@ extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const fl
                                  size_t workspace_bytes, int32_t passes, dssm_stream_t stream) {
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(dH) && aligned16(W) && aligned16(dA), DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
-    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(K, N) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
+    DSSM_REQUIRE(workspace && workspace_bytes >= image_bytes(K, N, R) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, DSSM_ERR_WORKSPACE,
                  "dssm_fc_bwd_dx (tc): workspace too small or unaligned");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = build_image(W, K, N, N, 0, (char*)workspace, st);  // B[n'=k_layer][k'=n_layer] = W[k_layer][n_layer]
+    int rc = build_image(W, K, N, N, 0, R, (char*)workspace, st);  // B[n'=k_layer][k'=n_layer] = W[k_layer][n_layer]
     if (rc != DSSM_OK) return rc;
     // D[M=R, N'=K] = A[M=R, K'=N] . B[N'=K, K'=N]^T
-    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K), 0, (const char*)workspace, passes};
+    tc::Args a{dH, nullptr, dA, nullptr, nullptr, nullptr, R, K, N, 0, DSSM_ACT_NONE, 0, tc::pick_bn(K, R), 0, (const char*)workspace, passes};
     return tc::launch(a, st);
 }
 
@@ -690,7 +709,7 @@ extern "C" int dssm_fc_bwd_dx_tc(const float* dH, int32_t R, int32_t N, const fl
 // as they lie in memory); `partials` receives [splits][K][N]; returns the split count through *splits_out.
 extern "C" size_t dssm_fc_bwd_dw_tc_workspace_bytes(int32_t R, int32_t K, int32_t N) {
     if (R <= 0 || K <= 0 || N <= 0) return 0;
-    const int tiles = cdiv(N, tc::pick_bn(N)) * cdiv(K, tc::BM);
+    const int tiles = cdiv(N, tc::pick_bn(N, 0)) * cdiv(K, tc::BM);
     return align_up((size_t)tc::pick_splits_tc(R, tiles) * K * N * sizeof(float), 256);
 }
 
@@ -700,7 +719,7 @@ extern "C" int dssm_fc_bwd_dw_tc(const float* Hprev, int32_t R, int32_t K, int32
     DSSM_REQUIRE(K % 4 == 0 && N % 4 == 0, DSSM_ERR_BAD_SHAPE, "tensor-core dense path needs K and N multiples of 4 (K=%d N=%d)", K, N);
     DSSM_REQUIRE(aligned16(Hprev) && aligned16(dH) && aligned16(partials) && (!scale || (aligned16(scale) && aligned16(shift))),
                  DSSM_ERR_BAD_ALIGN, "tensor-core dense path needs 16-byte aligned buffers");
-    const int bn = tc::pick_bn(N);
+    const int bn = tc::pick_bn(N, 0);  // dW: the parallelism comes from the split of the reduction over R
     const int tiles = cdiv(N, bn) * cdiv(K, tc::BM);
     const int splits = tc::pick_splits_tc(R, tiles);
     int kps = cdiv(R, splits);

@@ -6,6 +6,7 @@
 // the warp and broadcast with shuffles, and GATHER_UNROLL independent W1-row loads are in flight per
 // lane before the first FMA.  Algorithmic bytes: nnz*(4*L1+8) + R*4*L1 + (R+1)*4.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace dssm {
 
@@ -357,11 +358,13 @@ csc_fill_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 }
 
 // Row-order every column segment of the scratch CSC (tmp_row / tmp_val, slots as the atomics gave them) into
-// csc_row / csc_val.  Keys are unique inside a column, so rank(row) = number of set bits below `row` in the column's
-// row bitmap.  Small kernel: one warp per column -- <= 32 entries by comparison counting in registers, up to
-// SORT_WARP_MAX entries with a warp-private bitmap in shared memory; longer columns are queued for the block kernel.
-constexpr int SORT_WARP_MAX = 2048;
-constexpr int SORT_BIG_THREADS = 512;
+// csc_row / csc_val.  Keys are unique inside a column.  Small kernel: one warp per column of up to SORT_WARP_MAX entries,
+// ranks by comparison counting in registers (no shared memory: these kernels run on a side stream beside the tcgen05
+// GEMMs, whose CTAs leave ~10-30 KB of an SM's shared memory free -- a side kernel that needs more than that would keep
+// GEMM CTAs off every SM it touches); longer columns are queued for the block kernel, which ranks through a row bitmap
+// (rank(row) = number of set bits below `row`).
+constexpr int SORT_WARP_MAX = 128;  // = 4 entries per lane
+constexpr int SORT_BIG_THREADS = 256;
 
 __device__ __forceinline__ void bitmap_rank_scatter(const int* __restrict__ tmp_row, const float* __restrict__ tmp_val, int p,
                                                     int cnt, const uint32_t* bm, const int* pre, int* __restrict__ csc_row,
@@ -377,49 +380,41 @@ __device__ __forceinline__ void bitmap_rank_scatter(const int* __restrict__ tmp_
 
 __global__ void __launch_bounds__(SPMM_THREADS)
 csc_sort_small_kernel(const int* __restrict__ colcnt, const int* __restrict__ colptr, const int* __restrict__ tmp_row,
-                      const float* __restrict__ tmp_val, int* __restrict__ csc_row, float* __restrict__ csc_val, int D, int words,
+                      const float* __restrict__ tmp_val, int* __restrict__ csc_row, float* __restrict__ csc_val, int D,
                       int* __restrict__ big_ctl, int* __restrict__ big_list) {
-    extern __shared__ uint32_t sort_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint32_t* bm = sort_smem + (size_t)w * 2 * words;
-    int* pre = reinterpret_cast<int*>(bm + words);
     for (int c = blockIdx.x * wpb + w; c < D; c += gridDim.x * wpb) {
         const int cnt = __ldg(colcnt + c);
         if (cnt == 0) continue;
-        const int p = __ldg(colptr + c);
-        if (cnt <= 32) {
-            int r = 0x7fffffff;
-            float v = 0.f;
-            if (lane < cnt) { r = tmp_row[p + lane]; v = tmp_val[p + lane]; }
-            int rank = 0;
-            for (int j = 0; j < cnt; ++j) rank += __shfl_sync(0xffffffffu, r, j) < r ? 1 : 0;
-            if (lane < cnt) { csc_row[p + rank] = r; csc_val[p + rank] = v; }
-        } else if (cnt <= SORT_WARP_MAX) {
-            for (int i = lane; i < words; i += 32) bm[i] = 0u;
-            __syncwarp();
-            for (int i = lane; i < cnt; i += 32) {
-                const int r = tmp_row[p + i];
-                atomicOr(bm + (r >> 5), 1u << (r & 31));
-            }
-            __syncwarp();
-            // exclusive popcount prefix over the bitmap words: lane owns a contiguous run of words
-            const int per = (words + 31) / 32, lo = lane * per, hi = min(words, lo + per);
-            int sum = 0;
-            for (int i = lo; i < hi; ++i) sum += __popc(bm[i]);
-            int x = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            int run = x - sum;
-            for (int i = lo; i < hi; ++i) { pre[i] = run; run += __popc(bm[i]); }
-            __syncwarp();
-            bitmap_rank_scatter(tmp_row, tmp_val, p, cnt, bm, pre, csc_row, csc_val, lane, 32);
-            __syncwarp();
-        } else if (lane == 0) {
-            big_list[atomicAdd(big_ctl, 1)] = c;
+        if (cnt > SORT_WARP_MAX) {
+            if (lane == 0) big_list[atomicAdd(big_ctl, 1)] = c;
+            continue;
         }
+        const int p = __ldg(colptr + c);
+        constexpr int PER = SORT_WARP_MAX / 32;
+        int r[PER], rank[PER];
+        float v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = lane + 32 * j;
+            r[j] = 0x7fffffff;
+            v[j] = 0.f;
+            rank[j] = 0;
+            if (i < cnt) { r[j] = tmp_row[p + i]; v[j] = tmp_val[p + i]; }
+        }
+#pragma unroll
+        for (int jj = 0; jj < PER; ++jj) {
+            if (jj * 32 >= cnt) break;  // warp-uniform
+            const int lim = min(32, cnt - jj * 32);
+            for (int sl = 0; sl < lim; ++sl) {
+                const int key = __shfl_sync(0xffffffffu, r[jj], sl);
+#pragma unroll
+                for (int j = 0; j < PER; ++j) rank[j] += key < r[j] ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if (lane + 32 * j < cnt) { csc_row[p + rank[j]] = r[j]; csc_val[p + rank[j]] = v[j]; }
     }
 }
 
@@ -474,14 +469,33 @@ struct AdamW1 {
     int absent_done;        // ... unless dssm_spmm_bwd_adam_absent already gave it to them
 };
 
-template <int NCH>
+// 128-bit accesses that mark their L2 lines evict-first: the absent-column Adam streams ~0.3 GB of W1 / m / v once per step
+// beside the dense layers, whose 7 MB activation tensors must stay L2-resident
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_evict_first4(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_evict_first4(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+template <int NCH, bool STREAM = false>
 __device__ __forceinline__ void adam_row(const AdamW1& a, int c, int L4, int lane, const float4 (&g)[NCH], float lr_t) {
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
         const int col = lane + 32 * k;
         if (col < L4) {
             const size_t i = (size_t)c * L4 + col;
-            float4 pp = a.w[i], mm = a.m[i], vv = a.v[i];
+            float4 pp, mm, vv;
+            const uint64_t pol = STREAM ? l2_evict_first_policy() : 0;
+            if (STREAM) { pp = ld_evict_first4(a.w + i, pol); mm = ld_evict_first4(a.m + i, pol); vv = ld_evict_first4(a.v + i, pol); }
+            else { pp = a.w[i]; mm = a.m[i]; vv = a.v[i]; }
 #define ADAM1(x)                                               \
     {                                                          \
         const float gr = g[k].x;                               \
@@ -491,9 +505,8 @@ __device__ __forceinline__ void adam_row(const AdamW1& a, int c, int L4, int lan
     }
             ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
 #undef ADAM1
-            a.w[i] = pp;
-            a.m[i] = mm;
-            a.v[i] = vv;
+            if (STREAM) { st_evict_first4(a.w + i, pp, pol); st_evict_first4(a.m + i, mm, pol); st_evict_first4(a.v + i, vv, pol); }
+            else { a.w[i] = pp; a.m[i] = mm; a.v[i] = vv; }
         }
     }
 }
@@ -641,14 +654,14 @@ adam_absent_columns_kernel(int D, int L4, AdamW1 adam) {
 #pragma unroll
     for (int k = 0; k < NCH; ++k) zero[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < D; c += gridDim.x * wpb)
-        if (__ldg(adam.colcnt + c) == 0) adam_row<NCH>(adam, c, L4, lane, zero, lr_t);
+        if (__ldg(adam.colcnt + c) == 0) adam_row<NCH, true>(adam, c, L4, lane, zero, lr_t);
 }
 
 template <int NCH>
 static void launch_adam_absent(int D, int L1, const AdamW1& ad, cudaStream_t st) {
-    // two blocks per SM: the kernel has the whole dense stack to hide under, but the blocks it keeps resident take
-    // thread slots from the main stream's kernels (1024-thread BN blocks, 320-thread GEMM CTAs); 16 warps x 9 float4
-    // loads in flight per lane are still ~70 KB per SM, enough to stream
+    // two blocks per SM: the kernel has the dense stack to hide under, but the blocks it keeps resident take thread and
+    // register slots from the main stream's kernels (1024-thread BN blocks; a tcgen05 GEMM CTA is 320 threads x 136
+    // registers); 16 warps x 9 float4 loads in flight per lane are still ~70 KB per SM, enough to stream
     int blocks = sm_count() * 2;
     const int need = cdiv(D, SPMM_THREADS / 32);
     if (blocks > need) blocks = need;
@@ -729,6 +742,9 @@ static void launch_scatter(const int* indptr, const int* indices, const float* v
 
 // set by the tower's profiling step: recorded between the CSC build and the gather kernel
 thread_local cudaEvent_t g_spmm_bwd_mid_event = nullptr;
+// set by the tower around dssm_spmm_bwd_csc_build: recorded right after the column histogram, which is all that the
+// absent-column Adam needs -- it then runs on its own stream beside the rest of the build (scans, fill, row sort)
+thread_local cudaEvent_t g_csc_hist_done_event = nullptr;
 
 }  // namespace dssm
 
@@ -796,6 +812,7 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     const int nsm = sm_count();
     csc_hist_kernel<<<nsm * 8, 256, 0, st>>>(indptr, indices, R, w.colcnt);
     LAUNCH_CHECK("csc_hist");
+    if (g_csc_hist_done_event) CUDA_TRY(cudaEventRecord(g_csc_hist_done_event, st));
     const int scan_blocks = cdiv(D, SCAN_TILE);
     csc_scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(w.colcnt, D, w.colptr, w.itemptr, w.block_totals);
     LAUNCH_CHECK("csc_scan_local");
@@ -809,22 +826,18 @@ extern "C" int dssm_spmm_bwd_csc_build(const int32_t* indptr, const int32_t* ind
     LAUNCH_CHECK("csc_fill");
     // row-order the segments: fixed summation order in the gather (bit-reproducible dW1)
     const int words = cdiv(R, 32);
-    const size_t per_warp = (size_t)2 * words * sizeof(uint32_t);
-    int sort_wpb = (int)(((size_t)160 << 10) / per_warp);
-    DSSM_REQUIRE(sort_wpb >= 1, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_csc_build: R=%d rows exceed the row-bitmap sort (max %d)", R, (int)(((size_t)160 << 10) * 4));
-    if (sort_wpb > SPMM_THREADS / 32) sort_wpb = SPMM_THREADS / 32;
+    const size_t bm_bytes = (size_t)2 * words * sizeof(uint32_t);  // row bitmap + popcount prefix of the block kernel
+    DSSM_REQUIRE(bm_bytes <= ((size_t)160 << 10), DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_csc_build: R=%d rows exceed the row-bitmap sort (max %d)", R,
+                 (int)(((size_t)160 << 10) * 4));
     static PerDeviceOnce once;
-    if (once.need()) {
-        CUDA_TRY(cudaFuncSetAttribute(csc_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
-        CUDA_TRY(cudaFuncSetAttribute(csc_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
-    }
-    int sblocks = cdiv(D, sort_wpb);
+    if (once.need()) CUDA_TRY(cudaFuncSetAttribute(csc_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
+    int sblocks = cdiv(D, SPMM_THREADS / 32);
     if (sblocks > nsm * 8) sblocks = nsm * 8;
-    csc_sort_small_kernel<<<sblocks, sort_wpb * 32, (size_t)sort_wpb * per_warp, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row,
-                                                                                      w.csc_val, D, words, w.big_ctl, w.big_list);
+    csc_sort_small_kernel<<<sblocks, SPMM_THREADS, 0, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row, w.csc_val, D, w.big_ctl,
+                                                            w.big_list);
     LAUNCH_CHECK("csc_sort_small");
-    csc_sort_big_kernel<<<nsm, SORT_BIG_THREADS, per_warp, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row, w.csc_val, words,
-                                                                 w.big_ctl, w.big_list);
+    csc_sort_big_kernel<<<nsm * 2, SORT_BIG_THREADS, bm_bytes, st>>>(w.colcnt, w.colptr, w.tmp_row, w.tmp_val, w.csc_row, w.csc_val, words,
+                                                                     w.big_ctl, w.big_list);
     LAUNCH_CHECK("csc_sort_big");
     return DSSM_OK;
 }

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace dssm {
 
@@ -18,11 +19,12 @@ struct TensorInfo {
 static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
 
 extern thread_local cudaEvent_t g_spmm_bwd_mid_event;
+extern thread_local cudaEvent_t g_csc_hist_done_event;
 
 }  // namespace dssm
 // tensor-core dense path with prebuilt weight images (fc_tc.cu)
-extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx);
-extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, void* img, dssm_stream_t stream);
+extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx, int32_t R);
+extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, int32_t R, void* img, dssm_stream_t stream);
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                                   int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes, dssm_stream_t stream);
 extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes, dssm_stream_t stream);
@@ -130,6 +132,12 @@ struct dssm_tower {
     // The per-batch CSC of X depends only on the input batch: it is built on a side stream, forked at the start
     // of the training forward and joined right before the dW1 gather (also inside graph capture).
     cudaStream_t side;
+    // side2: the zero-gradient Adam of the W1 rows absent from the batch -- it needs only the column histogram, so it forks
+    //        off `side` right after csc_hist and no longer queues behind the scans / fill / row sort (or they behind it);
+    // side3: the dW GEMMs of the dense backward (independent of the dX chain once dh_l exists), joined before Adam.
+    cudaStream_t side2, side3;
+    cudaEvent_t ev_hist, ev_join2, ev_dh, ev_join3;
+    bool absent_forked, dw_forked;
     // pipelined host feed (dssm_tower_train_step_host_async): upload buffers k%2 filled on the copy stream
     cudaStream_t copy;
     cudaEvent_t ev_up_ready[2], ev_up_free[2], ev_step_done[2];
@@ -229,8 +237,8 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     for (int l = 2; l <= n; ++l) {
         t->img_fwd[l] = t->img_dx[l] = nullptr;
         if (is_tc_mode(t->cfg.gemm_mode)) {
-            t->img_fwd[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 0));
-            t->img_dx[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 1));
+            t->img_fwd[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 0, R));
+            t->img_dx[l] = a.take<char>(dssm_fc_tc_image_bytes(t->L[l - 1], t->L[l], 1, R));
         }
     }
     t->sp_ws_bytes = dssm_spmm_bwd_dw_workspace_bytes(R, t->D, t->L[1], max_nnz);
@@ -288,6 +296,9 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->graph_dp_exec = nullptr;
     t->launches_per_dp = 0;
     t->side = nullptr;
+    t->side2 = t->side3 = nullptr;
+    t->ev_hist = t->ev_join2 = t->ev_dh = t->ev_join3 = nullptr;
+    t->absent_forked = t->dw_forked = false;
     t->copy = nullptr;
     for (int b = 0; b < 2; ++b) t->ev_up_ready[b] = t->ev_up_free[b] = t->ev_step_done[b] = nullptr;
     t->feed_k = 0;
@@ -315,6 +326,10 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (t->ev_join) cudaEventDestroy(t->ev_join);
     if (t->ev_img) cudaEventDestroy(t->ev_img);
     if (t->side) cudaStreamDestroy(t->side);
+    if (t->side2) cudaStreamDestroy(t->side2);
+    if (t->side3) cudaStreamDestroy(t->side3);
+    for (cudaEvent_t e : {t->ev_hist, t->ev_join2, t->ev_dh, t->ev_join3})
+        if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) {
         if (t->ev_up_ready[b]) cudaEventDestroy(t->ev_up_ready[b]);
         if (t->ev_up_free[b]) cudaEventDestroy(t->ev_up_free[b]);
@@ -335,6 +350,8 @@ extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nn
     tmp.graph_dp = nullptr;
     tmp.graph_dp_exec = nullptr;
     tmp.side = nullptr;
+    tmp.side2 = tmp.side3 = nullptr;
+    tmp.ev_hist = tmp.ev_join2 = tmp.ev_dh = tmp.ev_join3 = nullptr;
     tmp.ev_fork = nullptr;
     tmp.ev_join = nullptr;
     tmp.ev_img = nullptr;
@@ -389,6 +406,12 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     CUDA_TRY(cudaMemset(t->dw_ws, 0, t->dw_ws_bytes));
     if (!t->side) {
         CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->side3, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_hist, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join2, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_dh, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join3, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_img, cudaEventDisableTiming));
@@ -474,8 +497,8 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     auto build_images = [&]() -> int {
         for (int l = 2; l <= n; ++l) {
             const std::string ls = std::to_string(l);
-            TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 0, t->img_fwd[l], (dssm_stream_t)aux));
-            if (train) TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 1, t->img_dx[l], (dssm_stream_t)aux));
+            TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 0, R, t->img_fwd[l], (dssm_stream_t)aux));
+            if (train) TRY(dssm_fc_tc_build_image(t->P_("W" + ls), t->L[l - 1], t->L[l], 1, R, t->img_dx[l], (dssm_stream_t)aux));
         }
         return DSSM_OK;
     };
@@ -490,13 +513,24 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         // dense layers that follow are latency-bound and leave most of the memory system idle
         CUDA_TRY(cudaEventRecord(t->ev_fork, main_st));
         CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
-        TRY(dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1],
-                                    (t->grads_p && !t->fuse_w1_adam) ? t->G_("W1") : nullptr, t->sp_ws, t->sp_ws_bytes,
-                                    (dssm_stream_t)t->side));
+        g_csc_hist_done_event = t->fuse_w1_adam ? t->ev_hist : nullptr;
+        const int rc_build = dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1],
+                                                     (t->grads_p && !t->fuse_w1_adam) ? t->G_("W1") : nullptr, t->sp_ws, t->sp_ws_bytes,
+                                                     (dssm_stream_t)t->side);
+        g_csc_hist_done_event = nullptr;
+        TRY(rc_build);
         if (t->fuse_w1_adam) {  // the rows of W1 this batch does not touch take their Adam step under the dense layers
             const int64_t wo = t->params[t->find(t->params, "W1")].off;
+            // Measured (profiles/r2_absent_adam_placement.txt): this kernel streams 0.3 GB and slows whatever latency-bound
+            // kernel runs beside it; started right after the histogram it sat on the first GEMM (+25..50 us on fc_fwd2),
+            // started after the CSC build it costs ~10 us spread over cos/loss and the first backward GEMMs.  So it waits
+            // for the end of the build (DSSM_ABSENT_EARLY=1 keeps the early start for experiments).
+            if (!getenv("DSSM_ABSENT_EARLY")) CUDA_TRY(cudaEventRecord(t->ev_hist, t->side));
+            CUDA_TRY(cudaStreamWaitEvent(t->side2, t->ev_hist, 0));
             TRY(dssm_spmm_bwd_adam_absent(t->D, t->L[1], t->params_p + wo, t->m_p + wo, t->v_p + wo, t->beta_pow_p, c.learning_rate,
-                                          c.beta1, c.beta2, c.adam_eps, t->sp_ws, t->sp_ws_bytes, (dssm_stream_t)t->side));
+                                          c.beta1, c.beta2, c.adam_eps, t->sp_ws, t->sp_ws_bytes, (dssm_stream_t)t->side2));
+            CUDA_TRY(cudaEventRecord(t->ev_join2, t->side2));
+            t->absent_forked = true;
         }
         CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
         t->csc_forked = true;
@@ -582,8 +616,17 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
             const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
             // under BN the bias gradient came out of dssm_bn_act_backward; without BN it is the column sum of dH
+            // dW_l needs dh_l and h_{l-1} only: under BN (no colsum sharing its workspace) it runs on side3 beside the dX chain
+            const bool fork_dw = c.use_bn && !(g_timer && g_timer->on) && getenv("DSSM_NO_DW_FORK") == nullptr;
+            dssm_stream_t dw_st = s;
+            if (fork_dw) {
+                CUDA_TRY(cudaEventRecord(t->ev_dh, (cudaStream_t)s));
+                CUDA_TRY(cudaStreamWaitEvent(t->side3, t->ev_dh, 0));
+                dw_st = (dssm_stream_t)t->side3;
+                t->dw_forked = true;
+            }
             TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
-                               c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, s));
+                               c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, dw_st));
             markf("fc_dw" + ls);
             if (is_tc_mode(c.gemm_mode) && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
                 TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], tc_passes_of(c.gemm_mode), s));
@@ -596,6 +639,8 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             mark(PH_DENSE_BWD);
             if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
                 CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join, 0));
+                if (t->absent_forked) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join2, 0));
+                t->absent_forked = false;
                 t->csc_forked = false;
                 mark(PH_CSC_BUILD);  // overlapped profile: time the main stream waited for the side stream
                 markf("join_side_stream");
@@ -623,6 +668,11 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             if (!c.use_bn) TRY(dssm_colsum(t->dh[1], R, t->L[1], t->G_("b1"), t->dw_ws, t->dw_ws_bytes, s));
             mark(PH_B1);
         }
+    }
+    if (t->dw_forked) {  // the dW GEMMs on side3 are done before anything downstream (Adam, gradient exchange) reads them
+        CUDA_TRY(cudaEventRecord(t->ev_join3, t->side3));
+        CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join3, 0));
+        t->dw_forked = false;
     }
     return DSSM_OK;
 }

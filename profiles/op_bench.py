@@ -41,8 +41,8 @@ def bench(label, fn, bytes_moved=None):
 for fn_name, args in (("dssm_fc_tc_image_bytes", None), ("dssm_fc_tc_build_image", None), ("dssm_fc_fwd_tc_img", None), ("dssm_fc_bwd_dx_tc_img", None)):
     getattr(lib, fn_name).restype = C.c_size_t if fn_name.endswith("bytes") else C.c_int
 i32, vp = C.c_int32, C.c_void_p
-lib.dssm_fc_tc_image_bytes.argtypes = [i32, i32, i32]
-lib.dssm_fc_tc_build_image.argtypes = [vp, i32, i32, i32, vp, vp]
+lib.dssm_fc_tc_image_bytes.argtypes = [i32, i32, i32, i32]
+lib.dssm_fc_tc_build_image.argtypes = [vp, i32, i32, i32, i32, vp, vp]
 lib.dssm_fc_fwd_tc_img.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp]
 lib.dssm_fc_bwd_dx_tc_img.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp]
 
@@ -52,10 +52,10 @@ for l in range(2, len(dims)):
     H, W, b = f32(R, K), f32(K, N) * 0.05, f32(N)
     sc, sh = f32(2, K).abs() + 0.5, f32(2, K)
     out, dH, dA = f32(R, N), f32(R, N), f32(R, K)
-    imgf = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 0), dtype=torch.uint8, device=dev)
-    imgx = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 1), dtype=torch.uint8, device=dev)
-    check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, p(imgf), st()))
-    check(lib.dssm_fc_tc_build_image(p(W), K, N, 1, p(imgx), st()))
+    imgf = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 0, R), dtype=torch.uint8, device=dev)
+    imgx = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 1, R), dtype=torch.uint8, device=dev)
+    check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, R, p(imgf), st()))
+    check(lib.dssm_fc_tc_build_image(p(W), K, N, 1, R, p(imgx), st()))
     bench(f"fc_fwd  tc img  [{R}x{K}]x[{K}x{N}]", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), PASSES, st())),
           4 * R * (K + N))
     bench(f"fc_dx   tc img  [{R}x{N}]x[{N}x{K}]", lambda: check(lib.dssm_fc_bwd_dx_tc_img(p(dH), R, N, p(imgx), K, p(dA), PASSES, st())), 4 * R * (K + N))
@@ -63,7 +63,7 @@ for l in range(2, len(dims)):
     dW, db = f32(K, N), f32(N)
     bench(f"fc_dw   tc      [{K}x{R}]x[{R}x{N}] (+reduce)",
           lambda: check(lib.dssm_fc_bwd_dw(p(H), R, K, B, p(sc), p(sh), 1, p(dH), N, p(dW), None, 1, p(ws), ws.numel(), st())), 4 * R * (K + N))
-    bench(f"image build x1  [{K}x{N}]", lambda: check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, p(imgf), st())))
+    bench(f"image build x1  [{K}x{N}]", lambda: check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, R, p(imgf), st())))
 for L in sorted(set(conf.layers)):
     X, dAl = f32(R, L), f32(R, L)
     state = ops.BNState(L, dev)
