@@ -300,6 +300,29 @@ syncbn_bwd_kernel(SyncBnPeers p, int n, int self, int point, int slot_floats, in
         for (int c = threadIdx.x; c < L; c += blockDim.x) db[c] = s_db[c] + s_db[L + c];
 }
 
+// ---- cross-GPU flags for the chunked dW1 exchange ----------------------------------------------------------------------
+// Every rank owns a peer-mapped flag block  [ flags u32[DSSM_MAX_PEERS] | epoch u32 ]  (zero-filled once).  A step's
+// sync points are numbered idx = 0 .. stride-1; rank r "signals idx" by writing  epoch*stride + idx + 1  into flags[r] of
+// EVERY rank's block (st.release.sys after a system-scope fence: everything this stream wrote before -- e.g. a chunk of
+// dW1 -- is visible to a peer that acquires the flag); "wait idx" spins until all n flags of the own block have reached
+// that value.  The epoch lives in device memory and is advanced by a kernel once per step, so the whole sequence replays
+// unchanged inside a CUDA graph.  Values only grow, so a rank that is already past a sync point never confuses a waiter.
+__global__ void peer_signal_kernel(SyncBnPeers p, int n, int self, int idx, int stride) {
+    __threadfence_system();
+    const uint32_t epoch = *reinterpret_cast<const uint32_t*>(p.buf[self] + DSSM_MAX_PEERS * sizeof(uint32_t));
+    const uint32_t value = epoch * (uint32_t)stride + (uint32_t)idx + 1u;
+    if ((int)threadIdx.x < n) st_release_sys(reinterpret_cast<uint32_t*>(p.buf[threadIdx.x]) + self, value);
+}
+__global__ void peer_wait_kernel(const uint32_t* own, int n, int idx, int stride) {
+    const uint32_t epoch = own[DSSM_MAX_PEERS];
+    const uint32_t value = epoch * (uint32_t)stride + (uint32_t)idx + 1u;
+    if ((int)threadIdx.x < n)
+        while ((int32_t)(ld_acquire_sys(own + threadIdx.x) - value) < 0) {
+        }
+    __syncthreads();
+}
+__global__ void peer_epoch_advance_kernel(uint32_t* own) { own[DSSM_MAX_PEERS] += 1u; }
+
 }  // namespace dssm
 
 using namespace dssm;
@@ -386,3 +409,32 @@ extern "C" int dssm_syncbn_backward(void* const* peer_bufs, int32_t n_ranks, int
     LAUNCH_CHECK("syncbn_bwd");
     return DSSM_OK;
 }
+
+// ---- flag synchronisation of the chunked exchange (public: include/dssm_b200.h) -----------------------------------------
+extern "C" size_t dssm_peer_flags_bytes(void) { return 256; }
+
+extern "C" int dssm_peer_signal(void* const* host_peer_flags, int32_t n_ranks, int32_t self, int32_t idx, int32_t stride, dssm_stream_t stream) {
+    SyncBnPeers p{};
+    int rc = syncbn_peers(host_peer_flags, n_ranks, self, &p);
+    if (rc != DSSM_OK) return rc;
+    DSSM_REQUIRE(idx >= 0 && idx < stride, DSSM_ERR_BAD_ARG, "dssm_peer_signal: idx=%d outside [0,%d)", idx, stride);
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, n_ranks, self, idx, stride);
+    LAUNCH_CHECK("peer_signal");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_peer_wait(const void* own_flags, int32_t n_ranks, int32_t idx, int32_t stride, dssm_stream_t stream) {
+    DSSM_REQUIRE(own_flags && n_ranks >= 1 && n_ranks <= DSSM_MAX_PEERS, DSSM_ERR_BAD_ARG, "dssm_peer_wait: bad arguments");
+    DSSM_REQUIRE(idx >= 0 && idx < stride, DSSM_ERR_BAD_ARG, "dssm_peer_wait: idx=%d outside [0,%d)", idx, stride);
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const uint32_t*)own_flags, n_ranks, idx, stride);
+    LAUNCH_CHECK("peer_wait");
+    return DSSM_OK;
+}
+
+extern "C" int dssm_peer_epoch_advance(void* own_flags, dssm_stream_t stream) {
+    DSSM_REQUIRE(own_flags, DSSM_ERR_BAD_ARG, "dssm_peer_epoch_advance: null pointer");
+    peer_epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint32_t*)own_flags);
+    LAUNCH_CHECK("peer_epoch_advance");
+    return DSSM_OK;
+}
+

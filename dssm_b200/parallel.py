@@ -8,6 +8,7 @@ statistics, so this equals averaging the statistics first).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -131,8 +132,6 @@ class DataParallelTower:
         self._peer_dw = arr(*[int(p) + 4 * w1_off for p in self._h_comm.buffer_ptrs])  # grads = comm[:P]
         has_mc = bool(getattr(self._h_params, "has_multicast_support", False)) and bool(self._h_params.multicast_ptr) \
             and bool(self._h_comm.multicast_ptr)
-        import os
-
         # measured (C2, profiles/r1_bench_c2_n{2,8}_*): at n = 2 the multicast path moves the same bytes as plain peer
         # loads/stores and its multimem instructions are ~15 % slower (0.557 vs 0.484 ms per step); at n = 8 it moves
         # 59 instead of 104 MB per direction and wins (0.543 vs 0.591 ms).  Default: NVLS at 8 ranks and up -- the sizes
@@ -143,9 +142,35 @@ class DataParallelTower:
         if self.use_multicast:
             self._mc_w = int(self._h_params.multicast_ptr) + 4 * w1_off
             self._mc_dw = int(self._h_comm.multicast_ptr) + 4 * w1_off
-        D = t.conf.TRIGRAM_D
-        per = (D + self.world - 1) // self.world
-        self.row_begin, self.row_end = min(self.rank * per, D), min((self.rank + 1) * per, D)
+        # flag block for the chunked exchange (csrc/nvlink.cu: peer_signal / peer_wait kernels)
+        from ._lib import lib
+
+        nb = int(lib.dssm_peer_flags_bytes())
+        self._flag_buf = symm_mem.empty(nb // 4, dtype=torch.int32, device=t.device).zero_()
+        self._h_flags = symm_mem.rendezvous(self._flag_buf, grp)
+        torch.cuda.synchronize(t.device)
+        dist.barrier(group=self.group)  # every block is zero before anybody's first flag can land in it
+        self._peer_flags = arr(*[int(p) for p in self._h_flags.buffer_ptrs])
+        self._xstream = torch.cuda.Stream(device=t.device)
+        # chunks of the exchange: the dW1 gather is issued in `x_chunks` column chunks, every chunk's rows are split over
+        # the ranks (rank r owns the r-th n-th of EVERY chunk), and chunk k is exchanged on a second stream while chunk
+        # k+1 is still being gathered
+        self.x_chunks = max(1, min(int(os.environ.get("DSSM_DP_CHUNKS", max(self.n_chunks, 4))), 32))
+        self._owned = [self._owned_rows(k) for k in range(self.x_chunks)]
+
+    def _chunk_cols(self, k: int):
+        """Column (= W1 row) range of chunk k of x_chunks -- the same split as dssm_tower_w1_chunk."""
+        D, n = self.tower.conf.TRIGRAM_D, self.x_chunks
+        per = ((D + n - 1) // n + 3) // 4 * 4
+        c0 = min(k * per, D)
+        return c0, min(c0 + per, D)
+
+    def _owned_rows(self, k: int, rank: Optional[int] = None):
+        """Rows of chunk k whose gradient this rank reduces, whose Adam state it keeps and whose new weights it pushes."""
+        r = self.rank if rank is None else rank
+        c0, c1 = self._chunk_cols(k)
+        per = (c1 - c0 + self.world - 1) // self.world
+        return min(c0 + r * per, c1), min(c0 + (r + 1) * per, c1)
 
     # ---- SyncBN: global-batch BatchNorm moments (csrc/nvlink.cu: syncbn_fwd_kernel / syncbn_bwd_kernel) ------------------
     def _setup_syncbn(self) -> None:
@@ -180,14 +205,14 @@ class DataParallelTower:
         if self.comm == "nvlink" and self.world > 1:
             L1 = t.conf.layers[0]
             D = t.conf.TRIGRAM_D
-            per = (D + self.world - 1) // self.world
             for buf in (t.m, t.v):
                 w = buf[:D * L1].view(D, L1)
-                for r in range(self.world):
-                    lo, hi = min(r * per, D), min((r + 1) * per, D)
-                    if hi > lo:
-                        dist.broadcast(w[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
-                                       group=self.group)
+                for k in range(self.x_chunks):
+                    for r in range(self.world):
+                        lo, hi = self._owned_rows(k, r)
+                        if hi > lo:
+                            dist.broadcast(w[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                           group=self.group)
         return t.state_dict()
 
     def save(self, path: str, vocabulary=None):
@@ -200,27 +225,52 @@ class DataParallelTower:
             dist.barrier(group=self.group)
         return out
 
-    def _step_staged_nvlink(self) -> None:
+    def _exchange_rows(self, lo: int, hi: int) -> None:
+        """Owner pass over the W1 rows [lo, hi): pull / reduce / Adam / push (csrc/nvlink.cu), on the current stream."""
         from ._lib import check, lib, ptr, stream_ptr
 
         t, c = self.tower, self.tower.conf
+        if hi <= lo:
+            return
+        if self.use_multicast:  # NVLS: in-switch reduction of the gradient rows, in-switch replication of the weight rows
+            check(lib.dssm_w1_shard_reduce_adam_mc(self._mc_dw, self._mc_w, ptr(t.params), self.world, c.TRIGRAM_D, c.layers[0],
+                                                   lo, hi, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate, c.beta1, c.beta2,
+                                                   c.adam_eps, stream_ptr()))
+        else:
+            check(lib.dssm_w1_shard_reduce_adam(self._peer_dw, self._peer_w, self.world, self.rank, c.TRIGRAM_D, c.layers[0],
+                                                lo, hi, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate, c.beta1, c.beta2,
+                                                c.adam_eps, stream_ptr()))
+
+    def _step_staged_nvlink(self) -> None:
+        """forward + dense backward + CSC (one C call / graph), then the dW1 gather in x_chunks column chunks on the main
+        stream; after chunk k a flag tells every peer that this rank's rows of the chunk are in (symmetric) memory, and the
+        owner pass of chunk k -- gated by a kernel that spins until ALL ranks have raised that flag -- runs on the exchange
+        stream under the gather of chunk k+1.  No host-side barrier: the two cross-device barriers of the un-chunked
+        exchange (27 + 12 us) become flag waits inside the streams, and the step stays one CUDA graph."""
+        from ._lib import check, lib, ptr, stream_ptr
+
+        t, K, n = self.tower, self.x_chunks, self.world
+        stride = K + 1
+        main = torch.cuda.current_stream(t.device)
+        own_flags = ptr(self._flag_buf)
         t.fwd_bwd_begin_staged()
         # [grads beyond W1 | EMA shadows]: small, stays on NCCL; queued now so that it runs beside the dW1 gather
         w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        t.backward_w1(0, 1)  # this rank's dense dW1, in symmetric memory
-        self._h_comm.barrier(channel=0)  # every rank's dW1 is complete and visible
-        if self.use_multicast:  # NVLS: in-switch reduction of the gradient rows, in-switch replication of the weight rows
-            check(lib.dssm_w1_shard_reduce_adam_mc(self._mc_dw, self._mc_w, ptr(t.params), self.world, c.TRIGRAM_D, c.layers[0],
-                                                   self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow),
-                                                   c.learning_rate, c.beta1, c.beta2, c.adam_eps, stream_ptr()))
-        else:
-            check(lib.dssm_w1_shard_reduce_adam(self._peer_dw, self._peer_w, self.world, self.rank, c.TRIGRAM_D, c.layers[0],
-                                                self.row_begin, self.row_end, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate,
-                                                c.beta1, c.beta2, c.adam_eps, stream_ptr()))
+        self._xstream.wait_stream(main)  # fork (also what puts the exchange stream inside a graph capture)
+        for k in range(K):
+            t.backward_w1(k, K)  # this rank's dense dW1 rows of chunk k, in symmetric memory
+            check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, k, stride, stream_ptr(main)))
+            with torch.cuda.stream(self._xstream):
+                check(lib.dssm_peer_wait(own_flags, n, k, stride, stream_ptr(self._xstream)))  # every rank's chunk k is complete
+                self._exchange_rows(*self._owned[k])
         w_rest.wait()
         t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
+        main.wait_stream(self._xstream)  # join: this rank's owner passes are done (beta powers were only read)
         t.adam_advance()
-        self._h_params.barrier(channel=0)  # every owner's rows have landed in every replica of W1
+        # every owner's rows have landed in every replica of W1 before anybody's next forward reads it
+        check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, K, stride, stream_ptr(main)))
+        check(lib.dssm_peer_wait(own_flags, n, K, stride, stream_ptr(main)))
+        check(lib.dssm_peer_epoch_advance(own_flags, stream_ptr(main)))
 
     # ---- one step on the staging CSR -------------------------------------------------------------------
     def _step_staged(self) -> None:

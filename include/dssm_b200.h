@@ -149,6 +149,18 @@ int dssm_w1_shard_reduce_adam_mc(const float* mc_dW1, float* mc_W1, const float*
                                  int32_t row_begin, int32_t row_end, float* m1, float* v1, const float* beta_pow, float lr,
                                  float beta1, float beta2, float eps, dssm_stream_t stream);
 
+/* Flag synchronisation between the ranks for a CHUNKED exchange (the dW1 gather is issued in column chunks; the owner
+ * kernels of chunk k run on a second stream as soon as every rank has finished that chunk, under the gather of chunk k+1).
+ * Every rank owns a peer-mapped, ZERO-FILLED block of dssm_peer_flags_bytes() bytes; host_peer_flags[r] addresses rank r's
+ * block.  A step has `stride` sync points idx = 0..stride-1.  dssm_peer_signal(idx): everything enqueued before it on
+ * `stream` is visible to any rank that passes dssm_peer_wait(idx) (fence + st.release.sys of a value that grows with a
+ * device-side epoch; ld.acquire.sys spin on the own block).  dssm_peer_epoch_advance once per step, after the last wait.
+ * All ranks must issue the same sequence; the three calls are graph-capturable. */
+size_t dssm_peer_flags_bytes(void);
+int dssm_peer_signal(void* const* host_peer_flags, int32_t n_ranks, int32_t self, int32_t idx, int32_t stride, dssm_stream_t stream);
+int dssm_peer_wait(const void* own_flags, int32_t n_ranks, int32_t idx, int32_t stride, dssm_stream_t stream);
+int dssm_peer_epoch_advance(void* own_flags, dssm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
  * (query segment rows [0,B), doc segment rows [B,R)) in one call.
