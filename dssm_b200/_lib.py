@@ -72,6 +72,9 @@ SIGNATURES = {
     "dssm_spmm_bwd_adam_absent": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _f, _f, _f, _f, _p, _sz, _p]),
     "dssm_w1_shard_reduce_adam": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _f, _f, _f, _p]),
     "dssm_w1_shard_reduce_adam_mc": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _f, _f, _f, _p]),
+    "dssm_w1_slots_reduce_adam": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _f, _f, _f, _p]),
+    "dssm_tower_set_w1_push": (C.c_int, [_p, _i32]),
+    "dssm_tower_backward_w1_push": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "dssm_peer_flags_bytes": (_sz, []),
     "dssm_peer_signal": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "dssm_peer_wait": (C.c_int, [_p, _i32, _i32, _i32, _p]),

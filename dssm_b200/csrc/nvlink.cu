@@ -78,6 +78,97 @@ w1_shard_reduce_adam_kernel(PeerPtrs p, int n_ranks, int self, int L4, int row_b
     }
 }
 
+// Owner pass of the PUSH exchange (spmm.cu: PushTarget): the gradient rows of the W1 rows this rank owns have been
+// written by every rank into this rank's LOCAL slot buffer [n_ranks][per][L1] (valid[r][row] == stamp iff rank r's batch
+// touched the row).  For each owned row: sum the valid slots in rank order, average, TF-Adam with the local m, v, and
+// replicate the new weight row into every rank's W1 -- peer stores, or ONE multimem.st through the NVSwitch multicast
+// mapping (mc_W != NULL).  All loads are local; the only NVLink traffic of this kernel is posted stores.
+template <int NCH, int NR, int ROWS>
+__global__ void __launch_bounds__(NV_THREADS)
+w1_slots_reduce_adam_kernel(const float4* __restrict__ slots, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ epoch,
+                            PeerPtrs p, float4* __restrict__ mc_W, int n_ranks, int self, int L4, int per, int row_begin, int row_end,
+                            float4* __restrict__ m, float4* __restrict__ v, const float* __restrict__ beta_pow, float lr, float b1, float b2,
+                            float eps) {
+    const float b1p = __ldg(beta_pow), b2p = __ldg(beta_pow + 1);
+    const float lr_t = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    const float inv_n = 1.0f / (float)n_ranks;
+    const uint32_t stamp = __ldg(epoch) + 1u;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int warp_global = blockIdx.x * wpb + (threadIdx.x >> 5), n_warps = gridDim.x * wpb;
+    for (int row0 = row_begin + warp_global * ROWS; row0 < row_end; row0 += n_warps * ROWS) {
+        bool ok[ROWS][NR];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                ok[j][r] = (row0 + j < row_end) && r < n_ranks && __ldcv(valid + (size_t)r * per + (row0 + j - row_begin)) == stamp;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int col = lane + 32 * k;
+            if (col >= L4) continue;
+            float4 part[ROWS][NR], pp[ROWS], mm[ROWS], vv[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+                for (int r = 0; r < NR; ++r)
+                    part[j][r] = ok[j][r] ? __ldcv(slots + ((size_t)r * per + (row0 + j - row_begin)) * L4 + col) : z4;
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const size_t i = (size_t)(row0 + j < row_end ? row0 + j : row0) * L4 + col;
+                pp[j] = p.W[self][i];
+                mm[j] = m[i];
+                vv[j] = v[i];
+            }
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                if (row0 + j >= row_end) continue;
+                const size_t i = (size_t)(row0 + j) * L4 + col;
+                float4 g = z4;
+#pragma unroll
+                for (int r = 0; r < NR; ++r)  // rank order; absent slots contribute exact zeros
+                    if (r < n_ranks) { g.x += part[j][r].x; g.y += part[j][r].y; g.z += part[j][r].z; g.w += part[j][r].w; }
+#define ADAM1(x)                                                   \
+    {                                                              \
+        const float gr = g.x * inv_n;                              \
+        mm[j].x = b1 * mm[j].x + (1.f - b1) * gr;                  \
+        vv[j].x = b2 * vv[j].x + (1.f - b2) * (gr * gr);           \
+        pp[j].x = pp[j].x - lr_t * mm[j].x / (sqrtf(vv[j].x) + eps); \
+    }
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                m[i] = mm[j];
+                v[i] = vv[j];
+                if (mc_W) {
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_W + i), "f"(pp[j].x), "f"(pp[j].y),
+                                 "f"(pp[j].z), "f"(pp[j].w)
+                                 : "memory");
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+                        if (r < n_ranks) p.W[r][i] = pp[j];
+                }
+            }
+        }
+    }
+}
+
+template <int NCH>
+static void launch_slots(const float* slots, const uint32_t* valid, const uint32_t* epoch, const PeerPtrs& p, float* mc_W, int n_ranks, int self,
+                         int L1, int per, int row_begin, int row_end, float* m, float* v, const float* beta_pow, float lr, float b1, float b2,
+                         float eps, cudaStream_t st) {
+    int blocks = sm_count() * 4;
+    const int need = cdiv(row_end - row_begin, NV_THREADS / 32);
+    if (blocks > need) blocks = need;
+#define SL_ARGS (const float4*)slots, valid, epoch, p, (float4*)mc_W, n_ranks, self, L1 / 4, per, row_begin, row_end, (float4*)m, (float4*)v, \
+                beta_pow, lr, b1, b2, eps
+    if (n_ranks <= 2) w1_slots_reduce_adam_kernel<NCH, 2, 4><<<blocks, NV_THREADS, 0, st>>>(SL_ARGS);
+    else if (n_ranks <= 4) w1_slots_reduce_adam_kernel<NCH, 4, 2><<<blocks, NV_THREADS, 0, st>>>(SL_ARGS);
+    else if (n_ranks <= 8) w1_slots_reduce_adam_kernel<NCH, 8, 1><<<blocks, NV_THREADS, 0, st>>>(SL_ARGS);
+    else w1_slots_reduce_adam_kernel<NCH, DSSM_MAX_PEERS, 1><<<blocks, NV_THREADS, 0, st>>>(SL_ARGS);
+#undef SL_ARGS
+}
+
 // NVLS variant: the buffers are also mapped through an NVSwitch MULTICAST address.  multimem.ld_reduce makes the switch
 // fetch the row from every replica and return the fp32 sum (one response instead of n), multimem.st makes it replicate
 // the new weight row into every replica (one store instead of n): per GPU and direction the wire carries
@@ -438,3 +529,30 @@ extern "C" int dssm_peer_epoch_advance(void* own_flags, dssm_stream_t stream) {
     return DSSM_OK;
 }
 
+
+// ---- owner pass of the push exchange (public: include/dssm_b200.h) ----------------------------------------------------
+extern "C" int dssm_w1_slots_reduce_adam(const float* slots, const uint32_t* valid, const uint32_t* epoch, float* const* peer_W1,
+                                         float* mc_W1, int32_t n_ranks, int32_t self, int32_t D, int32_t L1, int32_t per, float* m1,
+                                         float* v1, const float* beta_pow, float lr, float beta1, float beta2, float eps,
+                                         dssm_stream_t stream) {
+    DSSM_REQUIRE(slots && valid && epoch && peer_W1 && m1 && v1 && beta_pow, DSSM_ERR_BAD_ARG, "dssm_w1_slots_reduce_adam: null pointer");
+    DSSM_REQUIRE(n_ranks >= 1 && n_ranks <= DSSM_MAX_PEERS && self >= 0 && self < n_ranks, DSSM_ERR_BAD_ARG,
+                 "dssm_w1_slots_reduce_adam: n_ranks=%d self=%d (at most %d peers)", n_ranks, self, DSSM_MAX_PEERS);
+    DSSM_REQUIRE(D > 0 && L1 > 0 && L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_w1_slots_reduce_adam: bad shape");
+    DSSM_REQUIRE(per > 0 && (int64_t)per * n_ranks >= D, DSSM_ERR_BAD_ARG, "dssm_w1_slots_reduce_adam: per=%d does not cover D=%d", per, D);
+    PeerPtrs p{};
+    for (int r = 0; r < n_ranks; ++r) {
+        DSSM_REQUIRE(peer_W1[r] && aligned16(peer_W1[r]), DSSM_ERR_BAD_ALIGN, "dssm_w1_slots_reduce_adam: peer W1 %d null or unaligned", r);
+        p.W[r] = (float4*)peer_W1[r];
+    }
+    DSSM_REQUIRE(aligned16(slots) && aligned16(m1) && aligned16(v1) && (!mc_W1 || aligned16(mc_W1)), DSSM_ERR_BAD_ALIGN,
+                 "dssm_w1_slots_reduce_adam: buffers must be 16-byte aligned");
+    const int row_begin = self * per < D ? self * per : D;
+    const int row_end = row_begin + per < D ? row_begin + per : D;
+    if (row_begin == row_end) return DSSM_OK;
+    const int nch = cdiv(L1 / 4, 32);
+    DISPATCH_NCH(nch, launch_slots<N_>(slots, valid, epoch, p, mc_W1, n_ranks, self, L1, per, row_begin, row_end, m1, v1, beta_pow, lr, beta1,
+                                       beta2, eps, (cudaStream_t)stream));
+    LAUNCH_CHECK("w1_slots_reduce_adam");
+    return DSSM_OK;
+}

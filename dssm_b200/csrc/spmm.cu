@@ -511,6 +511,19 @@ __device__ __forceinline__ void adam_row(const AdamW1& a, int c, int L4, int lan
     }
 }
 
+// Data-parallel "push" output of the gather: instead of a local dense dW1 (which the owners would have to pull over
+// NVLink, one latency-bound round trip per row), every finished gradient row goes straight to the rank that OWNS the
+// row -- rank o owns the W1 rows [o*per, (o+1)*per) -- into slot [self][row - o*per] of that rank's peer-mapped slot
+// buffer [n_ranks][per][L1], together with a validity stamp (the step's epoch + 1).  Posted stores: the warp does not
+// wait for them, rows of columns absent from the batch are never written (no zero-fill, no traffic), and the exchange
+// needs only the owner pass over LOCAL memory afterwards (nvlink.cu: w1_slots_reduce_adam_kernel).
+struct PushTarget {
+    float4* slot[DSSM_MAX_PEERS];
+    uint32_t* valid[DSSM_MAX_PEERS];
+    const uint32_t* epoch;  // device: this step's epoch (own flag block)
+    int n_ranks, self, per;
+};
+
 // ASYNC: rows travel through the cp.async ring (best when dH is L2-resident and latency-bound, e.g. R = 6144);
 // otherwise through registers with GATHER_UNROLL loads in flight (measured faster when dH streams from HBM, R = 49152)
 template <int NCH, bool ASYNC, bool FUSE_ADAM>
@@ -519,9 +532,28 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                     const int* __restrict__ csc_row,
                     const float* __restrict__ csc_val, const float4* __restrict__ dH4, float4* __restrict__ dW4,
                     float4* __restrict__ partial4, int* __restrict__ done, int* __restrict__ next_item, int D, int L4,
-                    int col_begin, int col_end, AdamW1 adam, int* __restrict__ heavy_ctl /* {count, cursor} */,
-                    const int* __restrict__ heavy_list /* NULL: plain item order */) {
+                    int col_begin, int col_end, AdamW1 adam, const int* __restrict__ heavy_ctl /* {count} */,
+                    int* __restrict__ heavy_cursor /* this launch's cursor into the heavy list */, const int* __restrict__ heavy_list,
+                    PushTarget push) {
     extern __shared__ float4 ring_smem[];
+    const uint32_t stamp = push.n_ranks > 0 ? __ldg(push.epoch) + 1u : 0u;
+    // where the finished gradient row of column c goes: the local dense dW1, or the owner's slot buffer
+    auto store_row = [&](int c, const float4 (&acc)[NCH]) {
+        float4* dst;
+        if (push.n_ranks > 0) {
+            const int owner = c / push.per, local = c - owner * push.per;
+            const size_t slot_row = (size_t)push.self * push.per + local;
+            dst = push.slot[owner] + slot_row * L4;
+            if ((threadIdx.x & 31) == 0) push.valid[owner][slot_row] = stamp;
+        } else {
+            dst = dW4 + (size_t)c * L4;
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int col = (threadIdx.x & 31) + 32 * k;
+            if (col < L4) dst[col] = acc[k];
+        }
+    };
     float lr_t = 0.f;
     if (FUSE_ADAM) {
         const float b1p = __ldg(adam.beta_pow), b2p = __ldg(adam.beta_pow + 1);
@@ -535,9 +567,11 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
     const int item_lo = __ldg(itemptr + col_begin), n_items = __ldg(itemptr + col_end);
     (void)wpb; (void)stride; (void)D;
     // Dynamic work distribution (item costs range from 1 to CSC_CHUNK gathered rows; a static round-robin leaves half of
-    // the SMs idle behind the stragglers).  Two refinements: (1) the full-range gather first drains the "heavy" list --
-    // the items of multi-item columns, ~CSC_CHUNK rows each, half of all entries under a Zipf vocabulary -- so that
-    // their long dependent chains start at t = 0 instead of wherever column order put them; (2) the remaining
+    // the SMs idle behind the stragglers).  Two refinements: (1) every launch first drains the "heavy" list -- the items of
+    // multi-item columns, ~CSC_CHUNK rows each, half of all entries under a Zipf vocabulary -- so that their long
+    // dependent chains start at t = 0 and spread over the warps (a column-chunk launch takes the list items inside its
+    // range; without this a warp that grabbed ITEM_GRAB consecutive items of one hot column chained 4 x 128 rows and a
+    // quarter-range launch took as long as the full range); (2) the remaining
     // single-item columns are claimed ITEM_GRAB at a time: one same-address atomic per item caps the kernel at the
     // L2's serialised atomic rate.
     auto process = [&](int item, bool skip_multi) {
@@ -566,11 +600,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
             if (FUSE_ADAM) {
                 adam_row<NCH>(adam, c, L4, lane, acc, lr_t);
             } else {
-#pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    const int col = lane + 32 * k;
-                    if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
-                }
+                store_row(c, acc);
             }
         } else {
 #pragma unroll
@@ -602,24 +632,21 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
                 if (FUSE_ADAM) {
                     adam_row<NCH>(adam, c, L4, lane, acc, lr_t);
                 } else {
-#pragma unroll
-                    for (int k = 0; k < NCH; ++k) {
-                        const int col = lane + 32 * k;
-                        if (col < L4) dW4[(size_t)c * L4 + col] = acc[k];
-                    }
+                    store_row(c, acc);
                 }
                 if (lane == 0) done[c] = 0;  // leave the counters clean for the next step
             }
         }
     };
-    if (heavy_list) {
+    {   // heavy items first (every chunk scans the whole list and takes the items that fall into its range)
         const int nh = __ldg(heavy_ctl);
         for (;;) {
             int h = 0;
-            if (lane == 0) h = atomicAdd(heavy_ctl + 1, 1);
+            if (lane == 0) h = atomicAdd(heavy_cursor, 1);
             h = __shfl_sync(0xffffffffu, h, 0);
             if (h >= nh) break;
-            process(__ldg(heavy_list + h), false);
+            const int item = __ldg(heavy_list + h);
+            if (item >= item_lo && item < n_items) process(item, false);
         }
     }
     for (;;) {
@@ -628,7 +655,7 @@ dw_gather_v4_kernel(const int* __restrict__ colptr, const int* __restrict__ item
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_items) break;
         const int end = min(base + ITEM_GRAB, n_items);
-        for (int item = base; item < end; ++item) process(item, heavy_list != nullptr);
+        for (int item = base; item < end; ++item) process(item, true);
     }
     if (FUSE_ADAM && !adam.absent_done) {
         // columns absent from the batch: zero gradient, but m, v decay and w keeps moving on its momentum
@@ -683,7 +710,7 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
     w.colcnt = a.take<int>(D + 1);   // colcnt and done are contiguous: one memset clears both
     w.done = a.take<int>(D + 1);
     w.next_item = a.take<int>(MAX_W1_CHUNKS);  // one work counter per column chunk; cleared together with colcnt / done
-    w.heavy_ctl = a.take<int>(2);              // {heavy items, cursor}, cleared with them
+    w.heavy_ctl = a.take<int>(2 + MAX_W1_CHUNKS);  // {heavy items, -, one cursor per column chunk}, cleared with them
     w.big_ctl = a.take<int>(2);                // {columns queued for the block sort}, cleared with them
     w.colptr = a.take<int>(D + 1);
     w.cursor = a.take<int>(D + 1);
@@ -704,7 +731,9 @@ static CscWorkspace carve_csc(void* ws, int D, int L1, int64_t max_nnz) {
 
 template <int NCH>
 static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, int D, int L1, int col_begin, int col_end,
-                             int chunk, bool async, const AdamW1* adam, cudaStream_t st) {
+                             int chunk, bool async, const AdamW1* adam, cudaStream_t st, const PushTarget* push_to = nullptr) {
+    PushTarget push{};
+    if (push_to) push = *push_to;
     int blocks = sm_count() * 8;
     const int cols = col_end - col_begin;
     if (blocks > cols) blocks = cols > 0 ? cols : 1;
@@ -721,7 +750,7 @@ static void launch_dw_gather(const CscWorkspace& w, const float* dH, float* dW, 
             cudaFuncSetAttribute(dw_gather_v4_kernel<NCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
 #define DW_ARGS w.colptr, w.itemptr, w.item_rec, w.csc_row, w.csc_val, (const float4*)dH, (float4*)dW, (float4*)w.partial, w.done, \
-                w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad, w.heavy_ctl, (col_begin == 0 && col_end == D) ? w.heavy_list : nullptr
+                w.next_item + chunk, D, L1 / 4, col_begin, col_end, ad, w.heavy_ctl, w.heavy_ctl + 2 + chunk, w.heavy_list, push
     if (async && adam) dw_gather_v4_kernel<NCH, true, true><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
     else if (async) dw_gather_v4_kernel<NCH, true, false><<<blocks, SPMM_THREADS, smem, st>>>(DW_ARGS);
     else if (adam) dw_gather_v4_kernel<NCH, false, true><<<blocks, SPMM_THREADS, 0, st>>>(DW_ARGS);
@@ -858,6 +887,37 @@ extern "C" int dssm_spmm_bwd_dw_range(const float* dH, int32_t R, int32_t D, int
     const bool async = (size_t)R * L1 * sizeof(float) <= ((size_t)32 << 20);  // dH comfortably L2-resident
     DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, dW1, D, L1, col_begin, col_end, chunk, async, nullptr, (cudaStream_t)stream));
     LAUNCH_CHECK("dw_gather");
+    return DSSM_OK;
+}
+
+// Data-parallel gather with the rows PUSHED to their owners (see PushTarget): host arrays of n_ranks device pointers to
+// every rank's slot buffer [n_ranks][per][L1] and validity array [n_ranks][per]; epoch = the device word holding this
+// step's epoch (the flag block's).  The CSC must have been built with dW1 = NULL (no zero-fill is needed).
+extern "C" int dssm_spmm_bwd_dw_push(const float* dH, int32_t R, int32_t D, int32_t L1, float* const* host_peer_slots,
+                                     uint32_t* const* host_peer_valid, const uint32_t* epoch, int32_t n_ranks, int32_t self, int32_t per,
+                                     void* workspace, size_t workspace_bytes, dssm_stream_t stream) {
+    DSSM_REQUIRE(dH && host_peer_slots && host_peer_valid && epoch, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_push: null pointer");
+    DSSM_REQUIRE(n_ranks >= 1 && n_ranks <= DSSM_MAX_PEERS && self >= 0 && self < n_ranks, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_push: bad ranks");
+    DSSM_REQUIRE(L1 % 4 == 0 && L1 <= 1024, DSSM_ERR_BAD_SHAPE, "dssm_spmm_bwd_dw_push: bad L1");
+    DSSM_REQUIRE(per > 0 && (int64_t)per * n_ranks >= D, DSSM_ERR_BAD_ARG, "dssm_spmm_bwd_dw_push: per=%d does not cover D=%d over %d ranks", per, D, n_ranks);
+    PushTarget pt{};
+    for (int r = 0; r < n_ranks; ++r) {
+        DSSM_REQUIRE(host_peer_slots[r] && host_peer_valid[r] && aligned16(host_peer_slots[r]), DSSM_ERR_BAD_ALIGN,
+                     "dssm_spmm_bwd_dw_push: peer buffer %d null or unaligned", r);
+        pt.slot[r] = (float4*)host_peer_slots[r];
+        pt.valid[r] = host_peer_valid[r];
+    }
+    pt.epoch = epoch;
+    pt.n_ranks = n_ranks;
+    pt.self = self;
+    pt.per = per;
+    CscWorkspace w;
+    int rc = csc_from_workspace(D, L1, workspace, workspace_bytes, &w);
+    if (rc != DSSM_OK) return rc;
+    const int nch = cdiv(L1 / 4, 32);
+    const bool async = (size_t)R * L1 * sizeof(float) <= ((size_t)32 << 20);
+    DISPATCH_NCH(nch, launch_dw_gather<N_>(w, dH, nullptr, D, L1, 0, D, 0, async, nullptr, (cudaStream_t)stream, &pt));
+    LAUNCH_CHECK("dw_gather_push");
     return DSSM_OK;
 }
 

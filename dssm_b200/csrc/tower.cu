@@ -37,6 +37,9 @@ extern "C" int dssm_bn_bwd_reduce_only(const float* dA, const float* H, int32_t 
 extern "C" int dssm_bn_bwd_apply_only(float* dA, const float* H, int32_t R, int32_t L, int32_t B, int32_t act, const float* gamma,
                                       const float* mean, const float* rstd, const float* scale, const float* shift, const float* dgamma,
                                       const float* dbeta, dssm_stream_t stream);
+extern "C" int dssm_spmm_bwd_dw_push(const float* dH, int32_t R, int32_t D, int32_t L1, float* const* host_peer_slots,
+                                     uint32_t* const* host_peer_valid, const uint32_t* epoch, int32_t n_ranks, int32_t self, int32_t per,
+                                     void* workspace, size_t workspace_bytes, dssm_stream_t stream);
 extern "C" size_t dssm_syncbn_buffer_bytes(int32_t n_ranks, int32_t n_points, int32_t Lmax);
 extern "C" int dssm_syncbn_forward(void* const* peer_bufs, int32_t n_ranks, int32_t self, int32_t point, int32_t Lmax, int32_t L,
                                    const float* gamma, const float* beta, float* ema_mean, float* ema_var, float* mean, float* var,
@@ -115,6 +118,7 @@ struct dssm_tower {
     // SyncBN: global-batch moments over n replicas (dssm_tower_set_syncbn); 0 / 1 = per-replica moments
     int sync_n, sync_rank;
     void* sync_bufs[DSSM_MAX_PEERS];
+    bool w1_push;  // data-parallel push exchange: the gather writes no local dW1, so the CSC build need not zero-fill it
     float *Y, *qnorm, *dnorm, *cos_raw, *cos_sim, *prob, *loss_terms, *loss;
     void* img_fwd[DSSM_MAX_LAYERS + 1];  // pre-split weight images of layer l (tensor-core mode), rebuilt every step
     void* img_dx[DSSM_MAX_LAYERS + 1];
@@ -311,6 +315,7 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->fuse_w1_adam = false;
     t->sync_n = 0;
     t->sync_rank = 0;
+    t->w1_push = false;
     tower_carve(t, nullptr, 0);  // populate the workspace tensor table (offsets are final after bind)
     *out = t;
     return DSSM_OK;
@@ -515,8 +520,8 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
         CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
         g_csc_hist_done_event = t->fuse_w1_adam ? t->ev_hist : nullptr;
         const int rc_build = dssm_spmm_bwd_csc_build(indptr, indices, values, R, t->D, t->L[1],
-                                                     (t->grads_p && !t->fuse_w1_adam) ? t->G_("W1") : nullptr, t->sp_ws, t->sp_ws_bytes,
-                                                     (dssm_stream_t)t->side);
+                                                     (t->grads_p && !t->fuse_w1_adam && !t->w1_push) ? t->G_("W1") : nullptr, t->sp_ws,
+                                                     t->sp_ws_bytes, (dssm_stream_t)t->side);
         g_csc_hist_done_event = nullptr;
         TRY(rc_build);
         if (t->fuse_w1_adam) {  // the rows of W1 this batch does not touch take their Adam step under the dense layers
@@ -734,6 +739,23 @@ extern "C" int dssm_tower_backward_w1(dssm_tower* t, int32_t chunk, int32_t n_ch
     int c0, c1;
     w1_chunk_cols(t, chunk, n_chunks, &c0, &c1);
     return dssm_spmm_bwd_dw_range(t->dh[1], t->R, t->D, t->L[1], t->G_("W1"), c0, c1, chunk, t->sp_ws, t->sp_ws_bytes, stream);
+}
+
+extern "C" int dssm_tower_set_w1_push(dssm_tower* t, int32_t enabled) {
+    DSSM_REQUIRE(t, DSSM_ERR_BAD_ARG, "dssm_tower_set_w1_push: null tower");
+    if (t->graph_dp_exec) { cudaGraphExecDestroy(t->graph_dp_exec); t->graph_dp_exec = nullptr; }
+    if (t->graph_dp) { cudaGraphDestroy(t->graph_dp); t->graph_dp = nullptr; }
+    t->w1_push = enabled != 0;
+    return DSSM_OK;
+}
+
+extern "C" int dssm_tower_backward_w1_push(dssm_tower* t, float* const* host_peer_slots, uint32_t* const* host_peer_valid,
+                                           const uint32_t* epoch, int32_t n_ranks, int32_t self, int32_t per, dssm_stream_t stream) {
+    DSSM_REQUIRE(t && t->bound && t->grads_p, DSSM_ERR_STATE, "dssm_tower_backward_w1_push: tower not bound");
+    DSSM_REQUIRE(t->w1_push, DSSM_ERR_STATE, "dssm_tower_backward_w1_push: call dssm_tower_set_w1_push(t, 1) first");
+    LaunchScope ls(t);
+    return dssm_spmm_bwd_dw_push(t->dh[1], t->R, t->D, t->L[1], host_peer_slots, host_peer_valid, epoch, n_ranks, self, per, t->sp_ws,
+                                 t->sp_ws_bytes, stream);
 }
 
 extern "C" int dssm_tower_adam_range(dssm_tower* t, int64_t offset_floats, int64_t count_floats, float grad_scale,

@@ -155,8 +155,31 @@ class DataParallelTower:
         # chunks of the exchange: the dW1 gather is issued in `x_chunks` column chunks, every chunk's rows are split over
         # the ranks (rank r owns the r-th n-th of EVERY chunk), and chunk k is exchanged on a second stream while chunk
         # k+1 is still being gathered
-        self.x_chunks = max(1, min(int(os.environ.get("DSSM_DP_CHUNKS", max(self.n_chunks, 4))), 32))
+        # exchange = "push" (default): the gather writes every gradient row into its owner's slot buffer (posted peer
+        # stores under the gather itself, absent rows cost nothing), the owner pass reads local memory only;
+        # exchange = "pull": local dense dW1, owners pull the rows over NVLink (round 1's scheme, in column chunks)
+        self.exchange = os.environ.get("DSSM_DP_EXCHANGE", "push")
+        if self.exchange not in ("push", "pull"):
+            raise ValueError("DSSM_DP_EXCHANGE must be 'push' or 'pull'")
+        self.x_chunks = 1 if self.exchange == "push" else max(1, min(int(os.environ.get("DSSM_DP_CHUNKS", 2)), 32))
         self._owned = [self._owned_rows(k) for k in range(self.x_chunks)]
+        if self.exchange == "push":
+            import ctypes as C
+
+            from ._lib import check
+
+            D, L1 = t.conf.TRIGRAM_D, t.conf.layers[0]
+            self._per = (D + self.world - 1) // self.world
+            self._slots = symm_mem.empty(self.world * self._per * L1, dtype=torch.float32, device=t.device)
+            self._valid = symm_mem.empty(self.world * self._per, dtype=torch.int32, device=t.device).zero_()
+            self._h_slots = symm_mem.rendezvous(self._slots, grp)
+            self._h_valid = symm_mem.rendezvous(self._valid, grp)
+            torch.cuda.synchronize(t.device)
+            dist.barrier(group=self.group)
+            self._peer_slots = arr(*[int(p) for p in self._h_slots.buffer_ptrs])
+            self._peer_valid = arr(*[int(p) for p in self._h_valid.buffer_ptrs])
+            self._epoch_ptr = C.c_void_p(self._flag_buf.data_ptr() + 4 * 16)  # the epoch word behind the DSSM_MAX_PEERS flags
+            check(lib.dssm_tower_set_w1_push(t._h, 1))
 
     def _chunk_cols(self, k: int):
         """Column (= W1 row) range of chunk k of x_chunks -- the same split as dssm_tower_w1_chunk."""
@@ -168,6 +191,10 @@ class DataParallelTower:
     def _owned_rows(self, k: int, rank: Optional[int] = None):
         """Rows of chunk k whose gradient this rank reduces, whose Adam state it keeps and whose new weights it pushes."""
         r = self.rank if rank is None else rank
+        if getattr(self, "exchange", "pull") == "push":  # one contiguous block per rank
+            D = self.tower.conf.TRIGRAM_D
+            per = (D + self.world - 1) // self.world
+            return min(r * per, D), min((r + 1) * per, D)
         c0, c1 = self._chunk_cols(k)
         per = (c1 - c0 + self.world - 1) // self.world
         return min(c0 + r * per, c1), min(c0 + (r + 1) * per, c1)
@@ -241,6 +268,35 @@ class DataParallelTower:
                                                 lo, hi, ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate, c.beta1, c.beta2,
                                                 c.adam_eps, stream_ptr()))
 
+    def _step_staged_push(self) -> None:
+        """forward + dense backward + CSC (one C call / graph); the dW1 gather PUSHES every finished gradient row into the
+        slot buffer of the rank that owns the row (csrc/spmm.cu: PushTarget) -- the gradient's trip over NVLink happens
+        under the gather, as posted stores, and only for rows the batch touches; one flag round; the owner pass
+        (csrc/nvlink.cu: w1_slots_reduce_adam_kernel) sums its LOCAL slots in rank order, applies Adam and replicates the
+        new rows into every replica of W1 (peer stores, or multimem.st through the NVSwitch); one more flag round."""
+        from ._lib import check, lib, ptr, stream_ptr
+
+        t, c, n = self.tower, self.tower.conf, self.world
+        main = torch.cuda.current_stream(t.device)
+        own_flags = ptr(self._flag_buf)
+        t.fwd_bwd_begin_staged()
+        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        check(lib.dssm_tower_backward_w1_push(t._h, self._peer_slots, self._peer_valid, self._epoch_ptr, n, self.rank, self._per,
+                                              stream_ptr(main)))
+        check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, 0, 2, stream_ptr(main)))
+        check(lib.dssm_peer_wait(own_flags, n, 0, 2, stream_ptr(main)))  # every rank's rows for my shard have landed
+        check(lib.dssm_w1_slots_reduce_adam(ptr(self._slots), ptr(self._valid), self._epoch_ptr, self._peer_w,
+                                            self._mc_w if self.use_multicast else None, n, self.rank, c.TRIGRAM_D, c.layers[0], self._per,
+                                            ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate, c.beta1, c.beta2, c.adam_eps,
+                                            stream_ptr(main)))
+        w_rest.wait()
+        t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
+        t.adam_advance()
+        # every owner's rows have landed in every replica of W1 before anybody's next forward reads it
+        check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, 1, 2, stream_ptr(main)))
+        check(lib.dssm_peer_wait(own_flags, n, 1, 2, stream_ptr(main)))
+        check(lib.dssm_peer_epoch_advance(own_flags, stream_ptr(main)))
+
     def _step_staged_nvlink(self) -> None:
         """forward + dense backward + CSC (one C call / graph), then the dW1 gather in x_chunks column chunks on the main
         stream; after chunk k a flag tells every peer that this rank's rows of the chunk are in (symmetric) memory, and the
@@ -275,7 +331,7 @@ class DataParallelTower:
     # ---- one step on the staging CSR -------------------------------------------------------------------
     def _step_staged(self) -> None:
         if self.comm == "nvlink" and self.world > 1:
-            return self._step_staged_nvlink()
+            return self._step_staged_push() if self.exchange == "push" else self._step_staged_nvlink()
         t, n = self.tower, self.n_chunks
         t.fwd_bwd_begin_staged()
         if self.world == 1:

@@ -149,6 +149,18 @@ int dssm_w1_shard_reduce_adam_mc(const float* mc_dW1, float* mc_W1, const float*
                                  int32_t row_begin, int32_t row_end, float* m1, float* v1, const float* beta_pow, float lr,
                                  float beta1, float beta2, float eps, dssm_stream_t stream);
 
+/* PUSH exchange (default for N > 1): instead of a local dense dW1 that the owners pull, the dW1 gather writes every finished
+ * gradient row straight into the OWNER's peer-mapped slot buffer -- rank o owns the W1 rows [o*per, (o+1)*per); buffer
+ * layout [n_ranks][per][L1] floats, written at [self][row - o*per] -- with a validity stamp (epoch + 1; `epoch` = the device
+ * word of the flag block, see dssm_peer_*) in the owner's array [n_ranks][per] of uint32.  Rows of columns absent from the
+ * batch are not written at all (no zero-fill, no traffic).  After a flag round (all ranks' pushes visible), every rank runs
+ * dssm_w1_slots_reduce_adam over its own rows: valid slots summed in rank order (LOCAL loads), averaged, TF-Adam with the
+ * local m1 / v1, new weight row replicated into every rank's W1 (peer stores through peer_W1, or one multimem.st per 16
+ * bytes through the NVSwitch multicast mapping mc_W1 when it is not NULL). */
+int dssm_w1_slots_reduce_adam(const float* slots, const uint32_t* valid, const uint32_t* epoch, float* const* peer_W1, float* mc_W1,
+                              int32_t n_ranks, int32_t self, int32_t D, int32_t L1, int32_t per, float* m1, float* v1,
+                              const float* beta_pow, float lr, float beta1, float beta2, float eps, dssm_stream_t stream);
+
 /* Flag synchronisation between the ranks for a CHUNKED exchange (the dW1 gather is issued in column chunks; the owner
  * kernels of chunk k run on a second stream as soon as every rank has finished that chunk, under the gather of chunk k+1).
  * Every rank owns a peer-mapped, ZERO-FILLED block of dssm_peer_flags_bytes() bytes; host_peer_flags[r] addresses rank r's
@@ -352,6 +364,12 @@ int dssm_tower_adam(dssm_tower* t, float grad_scale, dssm_stream_t stream);
 int dssm_tower_backward_begin(dssm_tower* t, dssm_stream_t stream);
 int dssm_tower_backward_w1(dssm_tower* t, int32_t chunk, int32_t n_chunks, dssm_stream_t stream);
 int dssm_tower_w1_chunk(const dssm_tower* t, int32_t chunk, int32_t n_chunks, int64_t* offset_floats, int64_t* count_floats);
+/* Push exchange on the tower: dssm_tower_set_w1_push(t, 1) makes the CSC build skip the zero-fill of the local dW1;
+ * dssm_tower_backward_w1_push is the dW1 gather with the rows pushed to their owners (arguments as dssm_w1_slots_reduce_adam:
+ * HOST arrays of n_ranks device pointers to every rank's slot buffer and validity array). */
+int dssm_tower_set_w1_push(dssm_tower* t, int32_t enabled);
+int dssm_tower_backward_w1_push(dssm_tower* t, float* const* host_peer_slots, uint32_t* const* host_peer_valid, const uint32_t* epoch,
+                                int32_t n_ranks, int32_t self, int32_t per, dssm_stream_t stream);
 int dssm_tower_adam_range(dssm_tower* t, int64_t offset_floats, int64_t count_floats, float grad_scale, dssm_stream_t stream);
 int dssm_tower_adam_advance(dssm_tower* t, dssm_stream_t stream);
 /* Training forward + dssm_tower_backward_begin on the staging CSR; dssm_tower_capture_graph_dp turns that pair into
