@@ -5,6 +5,7 @@
 // (n, mean, M2) are merged by a fixed shuffle tree with Chan's formula -- no E[x^2]-E[x]^2 cancellation, and the
 // result is deterministic.
 #include "common.cuh"
+#include "bn_common.cuh"
 
 namespace dssm {
 
@@ -40,23 +41,6 @@ __device__ __forceinline__ bool last_block_of_strip(int* tickets, int n_blocks) 
     __syncthreads();
     if (s_last) __threadfence();
     return s_last;
-}
-
-struct BnFinalize {  // outputs of the forward finalize, all [2][L]
-    const float *gamma, *beta;
-    float *ema_mean, *ema_var, *mean, *var, *rstd, *scale, *shift;
-    float eps, decay;
-    int update_ema, nq_chunks;
-};
-
-__device__ __forceinline__ void bn_write_affine(const BnFinalize& f, int i, float mean, float var) {
-    const float rstd = 1.0f / sqrtf(var + f.eps);
-    const float sc = rstd * f.gamma[i];
-    f.mean[i] = mean;
-    f.var[i] = var;
-    f.rstd[i] = rstd;
-    f.scale[i] = sc;
-    f.shift[i] = f.beta[i] - mean * sc;
 }
 
 // The strip's partials [planes][n_chunks][32 columns] staged in shared memory by the whole block (one L2 round trip
@@ -144,25 +128,10 @@ bn_stats_kernel(const float* __restrict__ X, int R, int L, int B, float* __restr
     const int c1 = seg == 0 ? fin.nq_chunks : n_chunks_total;
     if (c0 == c1) return;  // empty segment (single-instance call, B == R)
     float cn = 0.f, mu = 0.f, m2 = 0.f;
-    for (int c = c0; c < c1; ++c) {
-        const float nb = s_part[(0 * n_chunks_total + c) * BN_TX + tx];
-        const float mb = s_part[(1 * n_chunks_total + c) * BN_TX + tx];
-        const float qb = s_part[(2 * n_chunks_total + c) * BN_TX + tx];
-        const float nt = cn + nb;
-        const float delta = mb - mu;
-        mu = mu + delta * (nb / nt);
-        m2 = m2 + qb + delta * delta * (cn * nb / nt);
-        cn = nt;
-    }
-    const int i = seg * L + col;
-    const float var = m2 / cn;  // biased (tf.nn.moments)
-    if (fin.update_ema) {
-        // ExponentialMovingAverage.apply: shadow -= (1 - decay) * (shadow - value), new_dssm.py:78-81
-        const float em = fin.ema_mean[i], ev = fin.ema_var[i];
-        fin.ema_mean[i] = em - (1.f - fin.decay) * (em - mu);
-        fin.ema_var[i] = ev - (1.f - fin.decay) * (ev - var);
-    }
-    bn_write_affine(fin, i, mu, var);
+    for (int c = c0; c < c1; ++c)
+        chan_merge(cn, mu, m2, s_part[(0 * n_chunks_total + c) * BN_TX + tx], s_part[(1 * n_chunks_total + c) * BN_TX + tx],
+                   s_part[(2 * n_chunks_total + c) * BN_TX + tx]);
+    bn_finalize_column(fin, seg * L + col, mu, m2 / cn);  // biased variance (tf.nn.moments)
 }
 
 // inference (new_dssm.py:85-86): the moments are the EMA shadows

@@ -19,6 +19,7 @@
 // tcgen05.commit releases a stage through an mbarrier, and the 8 warps drain TMEM with tcgen05.ld.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "bn_common.cuh"
 
 namespace dssm {
 namespace tc {
@@ -62,6 +63,7 @@ struct Args {
     int k_per_split;  // MN mode: rows of the reduction handled by one blockIdx.z (multiple of BK)
     const char* Bimg;  // K-major mode: pre-split, pre-swizzled image of B (make_b_image_kernel); NULL = stage B in registers
     int passes;        // 3: error-compensated 3xTF32 (1e-5 parity); 1: one tf32 MMA per product (DSSM_GEMM_TC_TF32)
+    FusedBnStats fbn;  // ws kernel: column moments of D taken in the epilogue (fbn.on)
 };
 
 // write one float4 (hi and lo parts) into a swizzled K-major tile: row r, 16-byte chunk c
@@ -512,6 +514,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
         const int row = m0 + lane_grp * 32 + lane;
         const int nchunks = BN / 32;
         const int nacc_e = nkb <= 12 ? 1 : (nkb < NACC ? nkb : NACC);
+        // scratch for the fused column moments: the pipeline stages are free once done_bar has completed
+        float* sc_n = reinterpret_cast<float*>(smem);
+        float* sc_mu = sc_n + 4 * MAX_BN;
+        float* sc_m2 = sc_mu + 4 * MAX_BN;
         for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
@@ -521,24 +527,120 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
             }
+            const int nb = n0 + ch * 32;
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]) + ((g.bias && nb + j < g.N) ? __ldg(g.bias + nb + j) : 0.f);
             if (row < g.M) {
-                const int nb = n0 + ch * 32;
                 float* out = g.D + (size_t)row * g.N + nb;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (nb + j + 3 < g.N) {
-                        float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
-                        if (g.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        *reinterpret_cast<float4*>(out + j) = o;
+                        *reinterpret_cast<float4*>(out + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
                     } else {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
+                            if (nb + j + q < g.N) out[j + q] = o[j + q];
                     }
+                }
+            }
+            if (g.fbn.on && !(g.fbn.on & 8)) {
+                // (count, mean, M2) of this warp's 32 rows for the 32 columns of the chunk: shifted by the warp's first row
+                // (no E[x^2] - E[x]^2 cancellation), then a butterfly transpose-reduce -- 31 shuffles per statistic leave
+                // lane j with the totals of column j
+                const bool valid = row < g.M;
+                const int n_w = __popc(__ballot_sync(0xffffffffu, valid));
+                float sq[32], kmine = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float kj = __shfl_sync(0xffffffffu, o[j], 0);
+                    if (lane == j) kmine = kj;
+                    const float d = valid ? o[j] - kj : 0.f;
+                    o[j] = d;
+                    sq[j] = d * d;
+                }
+#define XSTEP(OFF, NN)                                                            \
+    _Pragma("unroll") for (int i = 0; i < NN; ++i) {                              \
+        const bool up = (lane & OFF) != 0;                                        \
+        const float send_s = up ? o[i] : o[i + NN], keep_s = up ? o[i + NN] : o[i]; \
+        const float send_q = up ? sq[i] : sq[i + NN], keep_q = up ? sq[i + NN] : sq[i]; \
+        o[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, OFF);                \
+        sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, OFF);               \
+    }
+                XSTEP(16, 16) XSTEP(8, 8) XSTEP(4, 4) XSTEP(2, 2) XSTEP(1, 1)
+#undef XSTEP
+                const int cidx = lane_grp * MAX_BN + ch * 32 + lane;
+                if (n_w > 0) {
+                    const float md = o[0] / (float)n_w;
+                    sc_n[cidx] = (float)n_w;
+                    sc_mu[cidx] = kmine + md;
+                    sc_m2[cidx] = fmaxf(sq[0] - o[0] * md, 0.f);
+                } else {
+                    sc_n[cidx] = 0.f;
+                    sc_mu[cidx] = 0.f;
+                    sc_m2[cidx] = 0.f;
+                }
+            }
+        }
+        if (g.fbn.on && !(g.fbn.on & 4)) {
+            const int n_mtiles = gridDim.y;
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+            if (tid < BN && n0 + tid < g.N) {  // the tile's triple per column: lane groups merged in row order
+                float cn = 0.f, mu = 0.f, m2 = 0.f;
+#pragma unroll
+                for (int lg = 0; lg < 4; ++lg) chan_merge(cn, mu, m2, sc_n[lg * MAX_BN + tid], sc_mu[lg * MAX_BN + tid], sc_m2[lg * MAX_BN + tid]);
+                float* part = g.fbn.part;
+                part[((size_t)0 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = cn;
+                part[((size_t)1 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = mu;
+                part[((size_t)2 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = m2;
+            }
+            // "last CTA of this N tile finalizes" (same ticket scheme as bn.cu)
+            __shared__ int s_last;
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                const int prev = atomicAdd(g.fbn.tickets + blockIdx.x, 1);
+                s_last = prev == n_mtiles - 1;
+                if (s_last) g.fbn.tickets[blockIdx.x] = 0;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (s_last && !(g.fbn.on & 2)) {
+                // Finalize this N tile's columns.  The partials were written by other SMs, so every read is an L2 round
+                // trip: a thread-per-column serial merge over the M tiles costs one round trip per tile, and staging through
+                // a generic-pointer smem store per load serialises the same way (measured: +14..29 us per GEMM).  So: the 256
+                // threads pull [3][M tiles][BN] into the (now free) pipeline smem with 128-bit loads, STAGE_MLP of them in
+                // flight per thread before the first store, then one thread per (column, instance) merges its tiles in
+                // ascending order from shared memory -- fixed order, deterministic.  (n_mtiles <= 64: caller's contract.)
+                __threadfence();
+                const int nq = g.fbn.fin.nq_chunks;
+                float4* st4 = reinterpret_cast<float4*>(smem);
+                const float* st = reinterpret_cast<const float*>(smem);
+                const int bn4 = BN / 4;
+                const int total4 = 3 * n_mtiles * bn4;
+                const float* part = g.fbn.part;
+                constexpr int STAGE_MLP = 8;
+                for (int e0 = tid; e0 < total4; e0 += 256 * STAGE_MLP) {
+                    float4 v[STAGE_MLP];
+#pragma unroll
+                    for (int u = 0; u < STAGE_MLP; ++u) {
+                        const int e = e0 + u * 256;
+                        const int pc = e / bn4, c4 = e - pc * bn4;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e < total4 && n0 + c4 * 4 < g.N) v[u] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)pc * g.N + n0 + c4 * 4));
+                    }
+#pragma unroll
+                    for (int u = 0; u < STAGE_MLP; ++u)
+                        if (e0 + u * 256 < total4) st4[e0 + u * 256] = v[u];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int pr = tid; pr < 2 * BN; pr += 256) {
+                    const int seg = pr / BN, cl = pr - seg * BN, col = n0 + cl;
+                    const int c0 = seg == 0 ? 0 : nq, c1 = seg == 0 ? nq : n_mtiles;
+                    if (col >= g.N || c0 >= c1) continue;
+                    float cn = 0.f, mu = 0.f, m2 = 0.f;
+                    for (int c = c0; c < c1; ++c)
+                        chan_merge(cn, mu, m2, st[(0 * n_mtiles + c) * BN + cl], st[(1 * n_mtiles + c) * BN + cl], st[(2 * n_mtiles + c) * BN + cl]);
+                    bn_finalize_column(g.fbn.fin, seg * g.N + col, mu, m2 / cn);  // biased variance (tf.nn.moments)
                 }
             }
         }
@@ -662,10 +764,16 @@ extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx, i
 extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, int32_t R, void* img, dssm_stream_t stream) {
     return for_dx ? build_image(W, K, N, N, 0, R, (char*)img, (cudaStream_t)stream) : build_image(W, N, K, N, 1, R, (char*)img, (cudaStream_t)stream);
 }
+// fused_bn: NULL, or a dssm::FusedBnStats (host struct, bn_common.cuh) -- the epilogue then also takes the column moments
+// of Hout for the layer's two BN instances and the last CTA of every N tile finalizes them
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
                                   int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes,
-                                  dssm_stream_t stream) {
+                                  const void* fused_bn, dssm_stream_t stream) {
     tc::Args a{Hprev, nullptr, Hout, bias, scale, shift, R, N, K, 0, act, B, tc::pick_bn(N, R), 0, (const char*)img, passes};
+    if (fused_bn) {
+        DSSM_REQUIRE(K <= tc::WS_MAX_K - tc::BK, DSSM_ERR_BAD_SHAPE, "dssm_fc_fwd_tc_img: fused BN moments need the warp-specialised kernel (K <= %d)", tc::WS_MAX_K - tc::BK);
+        a.fbn = *reinterpret_cast<const FusedBnStats*>(fused_bn);
+    }
     return tc::launch(a, (cudaStream_t)stream);
 }
 extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes,

@@ -686,10 +686,12 @@ adam_absent_columns_kernel(int D, int L4, AdamW1 adam) {
 
 template <int NCH>
 static void launch_adam_absent(int D, int L1, const AdamW1& ad, cudaStream_t st) {
-    // two blocks per SM: the kernel has the dense stack to hide under, but the blocks it keeps resident take thread and
-    // register slots from the main stream's kernels (1024-thread BN blocks; a tcgen05 GEMM CTA is 320 threads x 136
-    // registers); 16 warps x 9 float4 loads in flight per lane are still ~70 KB per SM, enough to stream
-    int blocks = sm_count() * 2;
+    // ONE 256-thread block per SM.  The blocks are resident for the whole kernel (~100 us) and must leave room for the
+    // main stream's CTAs on every SM: a tcgen05 GEMM CTA is 320 threads x 144 registers (46 K of the 64 K), the MN-major
+    // dW CTA 256 x 199 (51 K); one block of this kernel holds 12 K, two hold 25 K -- with two resident, a GEMM launched
+    // while this kernel runs finds NO SM with room and waits for it to end (measured: fc_fwd3 17 -> 86 us when the timeline
+    // shifted so that they met).  8 warps x 9 float4 loads in flight per lane are ~36 KB per SM, enough to stream.
+    int blocks = getenv("DSSM_ABSENT_BLOCKS") ? sm_count() * atoi(getenv("DSSM_ABSENT_BLOCKS")) : sm_count();
     const int need = cdiv(D, SPMM_THREADS / 32);
     if (blocks > need) blocks = need;
     adam_absent_columns_kernel<NCH><<<blocks, SPMM_THREADS, 0, st>>>(D, L1 / 4, ad);

@@ -3,6 +3,7 @@
 // One C call per sess.run(train_step): no Python between the kernels, and the whole step can be captured
 // into a CUDA graph because every launch geometry depends only on (B, NEG, D, layers), never on nnz.
 #include "common.cuh"
+#include "bn_common.cuh"
 #include <string>
 #include <vector>
 #include <string.h>
@@ -26,7 +27,8 @@ extern thread_local cudaEvent_t g_csc_hist_done_event;
 extern "C" size_t dssm_fc_tc_image_bytes(int32_t K, int32_t N, int32_t for_dx, int32_t R);
 extern "C" int dssm_fc_tc_build_image(const float* W, int32_t K, int32_t N, int32_t for_dx, int32_t R, void* img, dssm_stream_t stream);
 extern "C" int dssm_fc_fwd_tc_img(const float* Hprev, int32_t R, int32_t K, int32_t B, const float* scale, const float* shift,
-                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes, dssm_stream_t stream);
+                                  int32_t act, const void* img, const float* bias, int32_t N, float* Hout, int32_t passes, const void* fused_bn,
+                                  dssm_stream_t stream);
 extern "C" int dssm_fc_bwd_dx_tc_img(const float* dH, int32_t R, int32_t N, const void* img, int32_t K, float* dA, int32_t passes, dssm_stream_t stream);
 static inline bool is_tc_mode(int mode) { return mode == DSSM_GEMM_TC_3XTF32 || mode == DSSM_GEMM_TC_TF32; }
 static inline int tc_passes_of(int mode) { return mode == DSSM_GEMM_TC_TF32 ? 1 : 3; }
@@ -126,6 +128,9 @@ struct dssm_tower {
     bool img_forked;
     void *bn_ws, *dw_ws, *sp_ws, *fc_ws;
     size_t bn_ws_bytes, dw_ws_bytes, sp_ws_bytes, fc_ws_bytes;
+    // BN moments taken in the producing GEMM's epilogue (fc_tc.cu, FusedBnStats): [tickets (256 B) | 3 x M tiles x maxL floats]
+    char* fbn_ws;
+    size_t fbn_ws_bytes;
     // last forward's CSR (backward reuses it)
     const int32_t *cur_indptr, *cur_indices;
     const float* cur_values;
@@ -224,6 +229,8 @@ static size_t tower_carve(dssm_tower* t, char* base, int64_t max_nnz) {
     for (int l = 1; l <= n; ++l) maxL = t->L[l] > maxL ? t->L[l] : maxL;
     t->bn_ws_bytes = dssm_bn_workspace_bytes(R, maxL);
     t->bn_ws = a.take<char>(t->bn_ws_bytes);
+    t->fbn_ws_bytes = 256 + (size_t)3 * ((R + 127) / 128) * maxL * sizeof(float);
+    t->fbn_ws = a.take<char>(t->fbn_ws_bytes);
     size_t dw = dssm_colsum_workspace_bytes(R, maxL);
     for (int l = 2; l <= n; ++l) {
         const size_t x = dssm_fc_bwd_dw_workspace_bytes(R, t->L[l - 1], t->L[l]);
@@ -408,6 +415,7 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     tower_carve(t, t->ws, max_nnz);
     // the reduction kernels keep self-resetting ticket counters at the head of their workspaces
     CUDA_TRY(cudaMemset(t->bn_ws, 0, t->bn_ws_bytes));
+    CUDA_TRY(cudaMemset(t->fbn_ws, 0, 256));
     CUDA_TRY(cudaMemset(t->dw_ws, 0, t->dw_ws_bytes));
     if (!t->side) {
         CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
@@ -544,14 +552,16 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
     markf("spmm_fwd");
     if (tc && timing) TRY(build_images());  // profiled step: serial, accounted to the dense forward
     if (t->img_forked) CUDA_TRY(cudaStreamWaitEvent(main_st, t->ev_img, 0));
+    bool stats_fused = false;  // BN moments of h[l] already taken (and finalized) by the GEMM that produced it
     for (int l = 1; l <= n; ++l) {
         const std::string ls = std::to_string(l);
         if (c.use_bn) {
             const bool sync = t->sync_n > 1 && on_train;  // the shadows then move with the GLOBAL moments, in the exchange kernel
-            TRY(dssm_bn_forward(t->h[l], R, t->L[l], B, on_train, sync ? 0 : update_ema, t->P_("bn" + ls + "_gamma"),
-                                t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
-                                c.bn_eps, c.ema_decay, t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l],
-                                t->bn_shift[l], t->bn_ws, t->bn_ws_bytes, s));
+            if (!stats_fused)
+                TRY(dssm_bn_forward(t->h[l], R, t->L[l], B, on_train, sync ? 0 : update_ema, t->P_("bn" + ls + "_gamma"),
+                                    t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
+                                    c.bn_eps, c.ema_decay, t->bn_mean[l], t->bn_var[l], t->bn_rstd[l], t->bn_scale[l],
+                                    t->bn_shift[l], t->bn_ws, t->bn_ws_bytes, s));
             if (sync)
                 TRY(dssm_syncbn_forward(t->sync_bufs, t->sync_n, t->sync_rank, l - 1, max_width(t), t->L[l], t->P_("bn" + ls + "_gamma"),
                                         t->P_("bn" + ls + "_beta"), t->E_("bn" + ls + "_ema_mean"), t->E_("bn" + ls + "_ema_var"),
@@ -559,13 +569,35 @@ static int tower_forward_impl(dssm_tower* t, const int32_t* indptr, const int32_
                                         update_ema, s));
             markf("bn_fwd" + ls);
         }
+        stats_fused = false;
         const float* sc = c.use_bn ? t->bn_scale[l] : nullptr;
         const float* sh = c.use_bn ? t->bn_shift[l] : nullptr;
         if (l < n) {
             const std::string ns = std::to_string(l + 1);
             if (tc && t->L[l] % 4 == 0 && t->L[l + 1] % 4 == 0) {
+                // training under BN: the epilogue of this GEMM also takes the batch moments of h[l+1] (both instances) and its
+                // last CTAs finalize them -- the separate bn_stats launch of the next layer disappears.  Needs B % 128 == 0
+                // (an M tile never straddles the query / doc boundary) and the warp-specialised kernel.
+                FusedBnStats fb{};
+                const bool fuse = c.use_bn && on_train && B % 128 == 0 && t->L[l] <= 512 - 32 && !timing && R <= 128 * 64 &&
+                                  getenv("DSSM_FUSED_BN") != nullptr;  // R bound: the finalize stages 3 x M tiles x BN floats in smem
+                // OFF by default -- measured (profiles/r2_fused_bn_epilogue.txt): the moments cost the epilogue +3 us, but the
+                // finalize by the LAST CTA of an N tile is a serial tail of 7-9 us (one L2 round trip to pull 48 tile triples,
+                // a 40-deep Chan merge per column), which is what the stand-alone bn_stats launch costs.  C2 step 0.354 ms
+                // with it, 0.351 ms without.  DSSM_FUSED_BN=1 turns it on (tests/test_gpu_tower.py runs both).
+                if (fuse) {
+                    const std::string pre = "bn" + ns + "_";
+                    const bool sync = t->sync_n > 1;
+                    fb.part = reinterpret_cast<float*>(t->fbn_ws + 256);
+                    fb.tickets = reinterpret_cast<int*>(t->fbn_ws);
+                    fb.fin = BnFinalize{t->P_(pre + "gamma"), t->P_(pre + "beta"), t->E_(pre + "ema_mean"), t->E_(pre + "ema_var"),
+                                        t->bn_mean[l + 1], t->bn_var[l + 1], t->bn_rstd[l + 1], t->bn_scale[l + 1], t->bn_shift[l + 1],
+                                        c.bn_eps, c.ema_decay, sync ? 0 : update_ema, B / 128};
+                    fb.on = 1;
+                }
                 TRY(dssm_fc_fwd_tc_img(t->h[l], R, t->L[l], B, sc, sh, c.act, t->img_fwd[l + 1], t->P_("b" + ns), t->L[l + 1],
-                                       t->h[l + 1], tc_passes_of(c.gemm_mode), s));
+                                       t->h[l + 1], tc_passes_of(c.gemm_mode), fuse ? &fb : nullptr, s));
+                stats_fused = fuse;
             } else {
                 TRY(dssm_fc_fwd(t->h[l], R, t->L[l], B, sc, sh, c.act, t->P_("W" + ns), t->P_("b" + ns), t->L[l + 1],
                                 t->h[l + 1], c.gemm_mode, t->fc_ws, t->fc_ws_bytes, s));

@@ -43,7 +43,7 @@ for fn_name, args in (("dssm_fc_tc_image_bytes", None), ("dssm_fc_tc_build_image
 i32, vp = C.c_int32, C.c_void_p
 lib.dssm_fc_tc_image_bytes.argtypes = [i32, i32, i32, i32]
 lib.dssm_fc_tc_build_image.argtypes = [vp, i32, i32, i32, i32, vp, vp]
-lib.dssm_fc_fwd_tc_img.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp]
+lib.dssm_fc_fwd_tc_img.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp, vp]
 lib.dssm_fc_bwd_dx_tc_img.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp]
 
 dims = [conf.TRIGRAM_D] + list(conf.layers)
@@ -56,7 +56,24 @@ for l in range(2, len(dims)):
     imgx = torch.zeros(lib.dssm_fc_tc_image_bytes(K, N, 1, R), dtype=torch.uint8, device=dev)
     check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, R, p(imgf), st()))
     check(lib.dssm_fc_tc_build_image(p(W), K, N, 1, R, p(imgx), st()))
-    bench(f"fc_fwd  tc img  [{R}x{K}]x[{K}x{N}]", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), PASSES, st())),
+    # fused BN column moments in the epilogue (FusedBnStats, bn_common.cuh): host struct built with ctypes
+    class BnFin(C.Structure):
+        _fields_ = [(n_, C.c_void_p) for n_ in ("gamma", "beta", "ema_mean", "ema_var", "mean", "var", "rstd", "scale", "shift")] + \
+                   [("eps", C.c_float), ("decay", C.c_float), ("update_ema", C.c_int), ("nq_chunks", C.c_int)]
+
+    class Fbn(C.Structure):
+        _fields_ = [("part", C.c_void_p), ("tickets", C.c_void_p), ("fin", BnFin), ("on", C.c_int)]
+
+    if B % 128 == 0:
+        z2 = lambda: f32(2, N)
+        keep = [z2() for _ in range(9)]
+        partb = torch.zeros(3 * ((R + 127) // 128) * N, device=dev)
+        tick = torch.zeros(64, dtype=torch.int32, device=dev)
+        for bits, lab in ((1, "fused BN moments"), (1 | 2, "  .. no finalize"), (1 | 4, "  .. no tile partial / ticket / finalize"), (1 | 8 | 4, "  .. nothing (flag only)")):
+            fb = Fbn(p(partb).value, p(tick).value, BnFin(*[p(k_).value for k_ in keep], 1e-3, 0.5, 1, B // 128), bits)
+            bench(f"fc_fwd  tc img  + {lab}", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), PASSES, C.byref(fb), st())),
+                  4 * R * (K + N))
+    bench(f"fc_fwd  tc img  [{R}x{K}]x[{K}x{N}]", lambda: check(lib.dssm_fc_fwd_tc_img(p(H), R, K, B, p(sc), p(sh), 1, p(imgf), p(b), N, p(out), PASSES, None, st())),
           4 * R * (K + N))
     bench(f"fc_dx   tc img  [{R}x{N}]x[{N}x{K}]", lambda: check(lib.dssm_fc_bwd_dx_tc_img(p(dH), R, N, p(imgx), K, p(dA), PASSES, st())), 4 * R * (K + N))
     ws = torch.zeros(lib.dssm_fc_bwd_dw_workspace_bytes(R, K, N), dtype=torch.uint8, device=dev)

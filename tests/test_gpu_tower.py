@@ -499,3 +499,33 @@ def test_full_size_baseline_configs_against_oracle(name):
     assert_close(t.tensor("Y").cpu().numpy(), c64["Y"], FWD_TOL, "Y")
     t.backward()
     assert_grads_close(conf, t.export_grads(), g64, allow, c64)
+
+
+def test_fused_bn_epilogue_matches_separate_bn_kernels(monkeypatch):
+    """DSSM_FUSED_BN=1: the tcgen05 GEMM epilogue takes the batch moments of its own output and its last CTAs finalize them
+    (csrc/fc_tc.cu, FusedBnStats).  Same oracle bounds as the default path on C2 (B % 128 == 0 is the fused path's condition),
+    and the two paths agree with each other to fp32 summation-order noise."""
+    from dssm_b200 import DSSMTower, baseline_config
+    from dssm_b200.synthetic import init_params, make_batch
+
+    conf = baseline_config("C2")
+    b = make_batch(conf, seed=5)
+    params = init_params(conf, 0)
+    X = b.to_scipy()
+    ref = DSSMTower(conf, max_nnz=b.nnz, params=params)
+    ref.forward(ref.to_device(b), on_train=True)
+    stats_ref = {k: ref.tensor(k).clone() for k in ("bn2_mean", "bn2_var", "bn3_mean", "bn3_var", "bn3_scale", "bn3_shift")}
+    n_ref = ref.launch_count
+    monkeypatch.setenv("DSSM_FUSED_BN", "1")
+    t = DSSMTower(conf, max_nnz=b.nnz, params=params)
+    loss = t.forward(t.to_device(b), on_train=True)
+    assert t.launch_count == n_ref - 2  # the bn_stats launches of layers 2 and 3 are gone
+    for k, v in stats_ref.items():
+        assert_close(t.tensor(k).cpu().numpy(), v.cpu().numpy(), 1e-5, f"fused {k}")
+    for k, v in t.export_ema().items():
+        assert_close(v, ref.export_ema()[k], 1e-5, f"fused ema {k}")
+    g64, allow, c64 = grad_tolerances(conf, X, params, GRAD_TOL, masks=gpu_relu_masks(conf, t))
+    assert abs(loss.item() - float(c64["loss"])) <= FWD_TOL * abs(float(c64["loss"]))
+    assert_close(t.tensor("Y").cpu().numpy(), c64["Y"], FWD_TOL, "Y")
+    t.backward()
+    assert_grads_close(conf, t.export_grads(), g64, allow, c64)
