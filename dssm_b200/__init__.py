@@ -14,7 +14,7 @@ from .ops import (  # noqa: F401
 )
 from .tower import DSSMTower  # noqa: F401
 from .parallel import DataParallelTower, shard_stacked_batch  # noqa: F401
-from .retrieval import corpus_topk, sharded_corpus_topk, topk_merge  # noqa: F401
+from .retrieval import CorpusIndex, corpus_topk, sharded_corpus_topk, topk_merge  # noqa: F401
 from .export import DeviceStreamingAUC, StreamingAUC, embed_docs, embed_queries, write_mid_vectors  # noqa: F401
 from .loader import HostBatchLoader  # noqa: F401
 from .vectorizer import CountVectorizerCompat, char_split  # noqa: F401

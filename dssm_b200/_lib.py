@@ -103,6 +103,10 @@ SIGNATURES = {
     "dssm_corpus_topk": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "dssm_corpus_topk_tc_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "dssm_corpus_topk_tc": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
+    "dssm_corpus_index_bytes": (_sz, [_i64, _i32]),
+    "dssm_corpus_index_build": (C.c_int, [_p, _i64, _i32, _p, _sz, _p]),
+    "dssm_corpus_topk_indexed_workspace_bytes": (_sz, [_i32, _i32]),
+    "dssm_corpus_topk_indexed": (C.c_int, [_p, _i32, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "dssm_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "dssm_tower_create": (C.c_int, [C.POINTER(dssm_config), C.POINTER(_p)]),
     "dssm_tower_destroy": (None, [_p]),

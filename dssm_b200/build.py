@@ -11,7 +11,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libdssm_b200.so"
-SOURCES = ["api.cu", "spmm.cu", "bn.cu", "fc.cu", "fc_tc.cu", "cosloss.cu", "adam.cu", "topk.cu", "topk_tc.cu", "nvlink.cu", "metrics.cu", "hostbatch.cu", "tower.cu"]
+SOURCES = ["api.cu", "spmm.cu", "bn.cu", "fc.cu", "fc_tc.cu", "cosloss.cu", "adam.cu", "topk.cu", "topk_tc.cu", "topk_bf16.cu", "nvlink.cu", "metrics.cu", "hostbatch.cu", "tower.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

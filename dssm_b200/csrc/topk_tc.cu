@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128)
 topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ docs /* row 0 = id id_base */, int id_base,
                            int d, const float* __restrict__ qn, const float* __restrict__ dn, int k, const int2* __restrict__ cand,
                            int* __restrict__ cand_cnt, float* __restrict__ run_s, int* __restrict__ run_i,
-                           int* __restrict__ run_cnt, float* __restrict__ tq) {
+                           int* __restrict__ run_cnt, float* __restrict__ tq, float margin /* bound on |approx - exact| of the filter */) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * 4 + w;
@@ -237,7 +237,7 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
             const int2 c2 = cand[(size_t)q * CAP + base + lane];
             cid0 = c2.x;
             const float approx = __int_as_float(c2.y);
-            alive = (cnt < k) || !(approx + MARGIN < ls[k - 1]);  // NaN approx (zero-norm doc) stays alive
+            alive = (cnt < k) || !(approx + margin < ls[k - 1]);  // NaN approx (zero-norm doc) stays alive
         }
         const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
         const int na = __popc(alive_mask);
@@ -305,7 +305,7 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
         cand_cnt[q] = 0;
         // threshold of the next filter pass, pre-multiplied by ||q||: keep iff dot >= (tau - margin) * ||q|| * ||d||
         const float tau = cnt == k ? ls[k - 1] : -INFINITY;
-        tq[q] = (tau - MARGIN) * nqv;
+        tq[q] = (tau - margin) * nqv;
     }
 }
 
@@ -335,6 +335,18 @@ static Ws carve(void* ws, int nq, int64_t nd, int k) {
 }
 
 }  // namespace tkc
+
+// rescoring + selection + next thresholds, shared by the tf32 (fp32 corpus) and bf16 (corpus index) filters
+int topk_rescore_select(const float* Q, int nq, const float* docs, int id_base, int d, const float* qn, const float* dn, int k,
+                        const int2* cand, int* cand_cnt, float* run_s, int* run_i, int* run_cnt, float* tq, float margin, cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.need()) CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t sel_smem = (size_t)4 * 2 * k * sizeof(float) + (size_t)4 * 33 * (d + 1) * sizeof(float);  // lists + per-warp row staging
+    tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_base, d, qn, dn, k, cand, cand_cnt, run_s, run_i, run_cnt,
+                                                                       tq, margin);
+    LAUNCH_CHECK("topk_rescore_select");
+    return DSSM_OK;
+}
 
 // exact path helpers (topk.cu)
 int topk_row_norms(const float* X, int64_t n, int d, float* out, cudaStream_t st);
@@ -367,10 +379,7 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     const int nq_pad = (nq + tkc::QT - 1) / tkc::QT * tkc::QT;
     static PerDeviceOnce once;
     const size_t smem = 3 * (size_t)tkc::TILE_BYTES + (size_t)tkc::THREADS * 32 * sizeof(float) + 1024;
-    if (once.need()) {
-        CUDA_TRY(cudaFuncSetAttribute(tkc::topk_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    }
+    if (once.need()) CUDA_TRY(cudaFuncSetAttribute(tkc::topk_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = topk_row_norms(Q, nq, d, w.qn, st);
     if (rc != DSSM_OK) return rc;
     rc = topk_row_norms(docs, nd, d, w.dn, st);
@@ -382,12 +391,9 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     const int seed = nd < tkc::SEED_DOCS ? (int)nd : tkc::SEED_DOCS;
     rc = topk_exact_chunk(Q, nq, docs, 0, seed, d, w.qn, w.dn, w.S, seed, id_offset, k, w.run_s, w.run_i, w.run_cnt, st);
     if (rc != DSSM_OK) return rc;
-    const size_t seed_smem = (size_t)4 * 2 * k * sizeof(float);
-    const size_t sel_smem = seed_smem + (size_t)4 * 33 * (d + 1) * sizeof(float);  // lists + per-warp row staging
     // thresholds from the seed (no candidates yet)
-    tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt,
-                                                                       w.run_s, w.run_i, w.run_cnt, w.tq);
-    LAUNCH_CHECK("topk_rescore_select(seed)");
+    rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
+    if (rc != DSSM_OK) return rc;
     const int n_qtiles = nq_pad / tkc::QT;
     int64_t lo = seed, chunk = 4 * (int64_t)tkc::SEED_DOCS;
     while (lo < nd) {
@@ -401,9 +407,8 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
         tkc::topk_tc_filter_kernel<<<grid, tkc::THREADS, smem, st>>>(Q, nq, docs, lo, hi, w.dn, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
                                                                      w.overflow, tps);
         LAUNCH_CHECK("topk_tc_filter");
-        tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand,
-                                                                           w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq);
-        LAUNCH_CHECK("topk_rescore_select");
+        rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
+        if (rc != DSSM_OK) return rc;
         lo = hi;
         chunk *= 4;
     }

@@ -310,6 +310,18 @@ size_t dssm_corpus_topk_tc_workspace_bytes(int32_t nq, int64_t nd, int32_t d, in
 int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs, int64_t nd, int32_t d, int32_t k, int32_t id_offset,
                         float* out_scores, int32_t* out_ids, int32_t* overflow_flag, void* workspace, size_t workspace_bytes,
                         dssm_stream_t stream);
+/* Corpus INDEX path (bf16 storage for the filter): dssm_corpus_index_build is run once per corpus and writes
+ * [fp32 row norms | the rows normalised, rounded to bf16 and laid out as SWIZZLE_128B tensor-core tiles] into `index`
+ * (dssm_corpus_index_bytes(nd, d) bytes, 1024-byte aligned; d must be 128).  dssm_corpus_topk_indexed then streams 256 B
+ * per document with one bulk copy per 128-doc tile, two resident query tiles per CTA (tcgen05.mma kind::f16, accumulators
+ * double-buffered in TMEM) and one compare per score; survivors are re-scored exactly from the fp32 rows `docs`, so ids and
+ * scores are bit-identical to dssm_corpus_topk.  *overflow_flag as for dssm_corpus_topk_tc. */
+size_t dssm_corpus_index_bytes(int64_t nd, int32_t d);
+int dssm_corpus_index_build(const float* docs, int64_t nd, int32_t d, void* index, size_t index_bytes, dssm_stream_t stream);
+size_t dssm_corpus_topk_indexed_workspace_bytes(int32_t nq, int32_t k);
+int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float* docs, const void* index, int64_t nd, int32_t d, int32_t k,
+                             int32_t id_offset, float* out_scores, int32_t* out_ids, int32_t* overflow_flag, void* workspace,
+                             size_t workspace_bytes, dssm_stream_t stream);
 int dssm_topk_merge(const float* part_scores, const int32_t* part_ids, int32_t n_parts, int32_t nq, int32_t k,
                     float* out_scores, int32_t* out_ids, dssm_stream_t stream);
 

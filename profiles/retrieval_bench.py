@@ -20,4 +20,18 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(f"nq={nq} nd={nd} k={k}: {ms:.3f} ms  {nd / ms * 1e3 / 1e6:.1f} M docs/s  fallback={rt.LAST_CALL['fallback']}")
+print(f"tf32 filter over the fp32 rows: nq={nq} nd={nd} k={k}: {ms:.3f} ms  {nd / ms * 1e3 / 1e6:.1f} M docs/s  fallback={rt.LAST_CALL['fallback']}")
+e0.record()
+index = rt.CorpusIndex(D)
+e1.record()
+torch.cuda.synchronize()
+print(f"index build: {e0.elapsed_time(e1):.3f} ms, {index.nbytes / 1e6:.0f} MB")
+rt.corpus_topk(Q, index, k)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps):
+    rt.corpus_topk(Q, index, k)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"bf16 filter over the corpus index: nq={nq} nd={nd} k={k}: {ms:.3f} ms  {nd / ms * 1e3 / 1e6:.1f} M docs/s  fallback={rt.LAST_CALL['fallback']}")

@@ -88,3 +88,48 @@ def test_topk_tensor_core_equals_exact_path_large():
     s4, i4 = corpus_topk(Qs, Ds, 50, method="tc")
     assert retrieval.LAST_CALL["method"] == "tc"  # may fall back on signed data; the result must be right either way
     assert torch.equal(i3, i4) and torch.equal(s3, s4)
+
+
+@pytest.mark.parametrize("nq,nd,k", [(64, 40000, 100), (130, 70001, 10), (300, 5000, 100), (7, 129, 50)])
+def test_topk_bf16_index_bit_exact_vs_oracle(nq, nd, k):
+    """CorpusIndex (normalised bf16 tile image, built once) + tcgen05 bf16 filter with two query tiles per CTA + exact fp32
+    rescoring: the oracle's ids and scores bit for bit -- ties across the seed / filter boundary, zero-norm docs and
+    queries, a corpus that is not a multiple of the 128-doc tile, a query count that is not a multiple of 256."""
+    from dssm_b200 import CorpusIndex, corpus_topk, retrieval
+    from oracle import corpus_topk_oracle
+
+    Q, D = make(nq, nd, 128, nq + nd)
+    D[nd - 5] = D[3]
+    if nd > 30000:
+        D[30000] = D[20000]
+        D[17000] = 0
+    D[100] = 0
+    Q[1] = Q[0]
+    if nq > 4:
+        Q[4] = 0
+    Dd = torch.from_numpy(D).cuda()
+    index = CorpusIndex(Dd)
+    assert index.nbytes >= 256 * nd
+    for rep in range(2):  # the index is reusable across query batches
+        s, i = corpus_topk(torch.from_numpy(Q).cuda(), index, k, id_offset=7)
+        assert retrieval.LAST_CALL == {"method": "bf16", "fallback": False}
+        rs, ri = corpus_topk_oracle(Q, D, k, id_offset=7)
+        assert np.array_equal(i.cpu().numpy(), ri)
+        assert np.array_equal(s.cpu().numpy(), rs)
+
+
+def test_topk_bf16_index_equals_exact_path_large_and_signed():
+    from dssm_b200 import CorpusIndex, corpus_topk, retrieval
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Q = torch.relu(torch.randn((512, 128), generator=g, device="cuda"))
+    D = torch.relu(torch.randn((300000, 128), generator=g, device="cuda"))
+    s1, i1 = corpus_topk(Q, D, 100, method="exact")
+    s2, i2 = corpus_topk(Q, CorpusIndex(D), 100)
+    assert retrieval.LAST_CALL == {"method": "bf16", "fallback": False}
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    Qs, Ds = torch.randn((128, 128), generator=g, device="cuda"), torch.randn((100000, 128), generator=g, device="cuda")
+    s3, i3 = corpus_topk(Qs, Ds, 50, method="exact")
+    s4, i4 = corpus_topk(Qs, CorpusIndex(Ds), 50)
+    assert retrieval.LAST_CALL["method"] == "bf16"
+    assert torch.equal(i3, i4) and torch.equal(s3, s4)
