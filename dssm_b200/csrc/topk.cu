@@ -10,6 +10,7 @@
 //                     inserts the rare survivors into a sorted list kept in shared memory
 // The corpus is processed in chunks so the score scratch stays bounded (workspace query).
 #include "common.cuh"
+#include "topk_common.cuh"
 #include <math.h>
 
 namespace dssm {
@@ -105,8 +106,10 @@ chunk_select_kernel(const float* __restrict__ S, int ldS, int nq, int cd, int id
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * 4 + w;
     if (q >= nq) return;
-    float* ls = sm + (size_t)w * 2 * k;
+    float* ls = sm + (size_t)w * 4 * k;  // two (score, id) list buffers per warp, ping-ponged by the batch merge
     int* li = reinterpret_cast<int*>(ls + k);
+    float* ls2 = ls + 2 * k;
+    int* li2 = reinterpret_cast<int*>(ls2 + k);
     int cnt = run_cnt[q];
     for (int i = lane; i < cnt; i += 32) {
         ls[i] = run_s[(size_t)q * k + i];
@@ -117,40 +120,7 @@ chunk_select_kernel(const float* __restrict__ S, int ldS, int nq, int cd, int id
     for (int base = 0; base < cd; base += 32) {
         const int j = base + lane;
         const float s = j < cd ? srow[j] : -INFINITY;
-        const float thr = cnt == k ? ls[k - 1] : -INFINITY;
-        const bool cand = j < cd && (cnt < k || s > thr);
-        unsigned mask = __ballot_sync(0xffffffffu, cand);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float cs = __shfl_sync(0xffffffffu, s, src);
-            const int cid = id0 + base + src;
-            // the threshold may have moved since the ballot
-            if (cnt == k && !(cs > ls[k - 1])) continue;
-            // position = number of entries that stay in front: score > cs, or equal score (their ids are smaller)
-            int ahead = 0;
-            for (int i = lane; i < cnt; i += 32) ahead += (ls[i] >= cs) ? 1 : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ahead += __shfl_xor_sync(0xffffffffu, ahead, o);
-            const int newcnt = cnt < k ? cnt + 1 : k;
-            // shift [ahead, newcnt-1) right by one: read, sync, write
-            float tmp_s[32];
-            int tmp_i[32];
-            int nt = 0;
-            for (int i = ahead + lane; i < newcnt - 1; i += 32) {
-                if (nt < 32) { tmp_s[nt] = ls[i]; tmp_i[nt] = li[i]; }
-                ++nt;
-            }
-            __syncwarp();
-            nt = 0;
-            for (int i = ahead + lane; i < newcnt - 1; i += 32) {
-                if (nt < 32) { ls[i + 1] = tmp_s[nt]; li[i + 1] = tmp_i[nt]; }
-                ++nt;
-            }
-            if (lane == 0) { ls[ahead] = cs; li[ahead] = cid; }
-            cnt = newcnt;
-            __syncwarp();
-        }
+        cnt = topk_merge_batch(ls, li, ls2, li2, cnt, k, s, id0 + j, j < cd, lane);
     }
     for (int i = lane; i < cnt; i += 32) {
         run_s[(size_t)q * k + i] = ls[i];
@@ -218,6 +188,13 @@ static TopkWs carve_topk(void* ws, int nq, int64_t nd, int k) {
 }
 
 // host helpers shared with the tensor-core path (topk_tc.cu)
+// two [k] (score, id) lists per warp: 64 KB per block at the largest k (1024)
+static cudaError_t chunk_select_attr() {
+    static PerDeviceOnce once;
+    if (!once.need()) return cudaSuccess;
+    return cudaFuncSetAttribute(chunk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
+}
+
 int topk_row_norms(const float* X, int64_t n, int d, float* out, cudaStream_t st) {
     row_norm_seq_kernel<<<cdiv(n, 128), 128, 0, st>>>(X, n, d, out);
     LAUNCH_CHECK("row_norm_seq");
@@ -228,7 +205,8 @@ int topk_exact_chunk(const float* Q, int nq, const float* docs, int64_t doc0, in
     dim3 grid(cdiv(cd, TK_DT), cdiv(nq, TK_QT));
     exact_scores_kernel<<<grid, 256, 0, st>>>(Q, nq, docs, doc0, cd, d, qn, dn, S, ldS);
     LAUNCH_CHECK("exact_scores");
-    chunk_select_kernel<<<cdiv(nq, 4), 128, (size_t)4 * 2 * k * sizeof(float), st>>>(S, ldS, nq, cd, id0, k, run_s, run_i, run_cnt);
+    CUDA_TRY(chunk_select_attr());
+    chunk_select_kernel<<<cdiv(nq, 4), 128, (size_t)4 * 4 * k * sizeof(float), st>>>(S, ldS, nq, cd, id0, k, run_s, run_i, run_cnt);
     LAUNCH_CHECK("chunk_select");
     return DSSM_OK;
 }
@@ -260,7 +238,8 @@ extern "C" int dssm_corpus_topk(const float* Q, int32_t nq, const float* docs, i
     LAUNCH_CHECK("row_norm_seq(docs)");
     CUDA_TRY(cudaMemsetAsync(w.run_cnt, 0, (size_t)nq * sizeof(int), st));
     const int chunk = nd < TK_CHUNK ? (int)nd : TK_CHUNK;
-    const size_t sel_smem = (size_t)4 * 2 * k * sizeof(float);
+    const size_t sel_smem = (size_t)4 * 4 * k * sizeof(float);
+    CUDA_TRY(chunk_select_attr());
     for (int64_t d0 = 0; d0 < nd; d0 += chunk) {
         const int cd = (int)((nd - d0) < chunk ? (nd - d0) : chunk);
         dim3 grid(cdiv(cd, TK_DT), cdiv(nq, TK_QT));

@@ -19,6 +19,7 @@
 // corpus -- no conversion pass, no extra copy of the corpus.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "topk_common.cuh"
 #include <math.h>
 
 namespace dssm {
@@ -212,8 +213,10 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * 4 + w;
     if (q >= nq) return;
-    float* ls = sm + (size_t)w * 2 * k;
+    float* ls = sm + (size_t)w * 4 * k;  // two (score, id) list buffers per warp, ping-ponged by the batch merge
     int* li = reinterpret_cast<int*>(ls + k);
+    float* ls2 = ls + 2 * k;
+    int* li2 = reinterpret_cast<int*>(ls2 + k);
     int cnt = run_cnt[q];
     for (int i = lane; i < cnt; i += 32) {
         ls[i] = run_s[(size_t)q * k + i];
@@ -222,15 +225,17 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
     __syncwarp();
     const int n = min(cand_cnt[q], CAP);
     const float nqv = qn[q];
-    // per-warp staging: the query row and 32 candidate rows (row stride d+1 words: conflict-free column walks), so the
-    // global reads are coalesced 512-byte rows while every lane still sums ITS candidate strictly in t order
-    float* sq = reinterpret_cast<float*>(sm + (size_t)4 * 2 * k) + (size_t)w * (33 * (d + 1));
-    float* srow = sq + (d + 1);
+    // per-warp staging of the query row only.  Every lane then walks ITS candidate's fp32 row straight from L2 with
+    // 128-bit loads, 8 in flight, and sums strictly in t order (the oracle's arithmetic).  (Round 1 staged 32 candidate
+    // rows per warp in shared memory: 17 KB per warp capped the SM at 12 warps, and ncu showed the kernel issue-bound at
+    // 33 % issue utilisation with 15 % of the warp slots filled -- the rows are L2 hits (84 %), DRAM is idle.)
+    float* sq = reinterpret_cast<float*>(sm + (size_t)4 * 4 * k) + (size_t)w * (d + 4);
     for (int t = lane; t < d; t += 32) sq[t] = __ldg(Q + (size_t)q * d + t);
     __syncwarp();
+    const bool vec = (d % 32 == 0);
     for (int base = 0; base < n; base += 32) {
         // candidates whose approximate cosine cannot reach the current k-th best any more are dropped before the
-        // (expensive) exact scoring: |approx - exact| <= MARGIN, and the k-th best only rises
+        // (expensive) exact scoring: |approx - exact| <= margin, and the k-th best only rises
         int cid0 = 0x7fffffff;
         bool alive = false;
         if (base + lane < n) {
@@ -246,55 +251,36 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
         const int src_lane = lane < na ? __fns(alive_mask, 0, lane + 1) : 0;
         int cid = __shfl_sync(0xffffffffu, cid0, src_lane);
         if (lane >= na) cid = 0x7fffffff;
-        for (int c = 0; c < na; ++c) {
-            const int id = __shfl_sync(0xffffffffu, cid, c);
-            const float* drow = docs + (size_t)(id - id_base) * d;
-            for (int t = lane; t < d; t += 32) srow[c * (d + 1) + t] = __ldg(drow + t);
-        }
-        __syncwarp();
         float s = -INFINITY;
         if (lane < na) {
-            const float* mine = srow + lane * (d + 1);
+            const float* mine = docs + (size_t)(cid - id_base) * d;
             float acc = 0.f;
-            for (int t = 0; t < d; ++t) acc = __fadd_rn(acc, __fmul_rn(sq[t], mine[t]));
+            if (vec) {
+                const float4* m4 = reinterpret_cast<const float4*>(mine);
+                for (int t0 = 0; t0 < d; t0 += 32) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldg(m4 + (t0 >> 2) + u);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 qv = *reinterpret_cast<const float4*>(sq + t0 + 4 * u);
+                        acc = __fadd_rn(acc, __fmul_rn(qv.x, v[u].x));
+                        acc = __fadd_rn(acc, __fmul_rn(qv.y, v[u].y));
+                        acc = __fadd_rn(acc, __fmul_rn(qv.z, v[u].z));
+                        acc = __fadd_rn(acc, __fmul_rn(qv.w, v[u].w));
+                    }
+                }
+            } else {
+                for (int t = 0; t < d; ++t) acc = __fadd_rn(acc, __fmul_rn(sq[t], __ldg(mine + t)));
+            }
             s = __fdiv_rn(acc, __fmul_rn(nqv, dn[cid - id_base]));
             if (s != s) s = -INFINITY;
             s = s + 0.0f;
         }
         __syncwarp();
-        unsigned mask = __ballot_sync(0xffffffffu, lane < na);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float cs = __shfl_sync(0xffffffffu, s, src);
-            const int ci = __shfl_sync(0xffffffffu, cid, src);
-            if (cnt == k) {  // must beat the current worst under (score desc, id asc)
-                const float wsc = ls[k - 1];
-                const int wid = li[k - 1];
-                if (!(cs > wsc || (cs == wsc && ci < wid))) continue;
-            }
-            int ahead = 0;
-            for (int i = lane; i < cnt; i += 32) ahead += (ls[i] > cs || (ls[i] == cs && li[i] < ci)) ? 1 : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ahead += __shfl_xor_sync(0xffffffffu, ahead, o);
-            const int newcnt = cnt < k ? cnt + 1 : k;
-            float tmp_s[32];
-            int tmp_i[32];
-            int nt = 0;
-            for (int i = ahead + lane; i < newcnt - 1; i += 32) {
-                if (nt < 32) { tmp_s[nt] = ls[i]; tmp_i[nt] = li[i]; }
-                ++nt;
-            }
-            __syncwarp();
-            nt = 0;
-            for (int i = ahead + lane; i < newcnt - 1; i += 32) {
-                if (nt < 32) { ls[i + 1] = tmp_s[nt]; li[i + 1] = tmp_i[nt]; }
-                ++nt;
-            }
-            if (lane == 0) { ls[ahead] = cs; li[ahead] = ci; }
-            cnt = newcnt;
-            __syncwarp();
-        }
+        // merge the batch into the running list in one step (topk_common.cuh; round 1 inserted candidate by candidate, a
+        // warp-wide O(k) shift each: ~120 instructions x ~250 insertions per query and pass made the kernel issue-bound)
+        cnt = topk_merge_batch(ls, li, ls2, li2, cnt, k, s, cid, lane < na, lane);
     }
     for (int i = lane; i < cnt; i += 32) {
         run_s[(size_t)q * k + i] = ls[i];
@@ -341,7 +327,7 @@ int topk_rescore_select(const float* Q, int nq, const float* docs, int id_base, 
                         const int2* cand, int* cand_cnt, float* run_s, int* run_i, int* run_cnt, float* tq, float margin, cudaStream_t st) {
     static PerDeviceOnce once;
     if (once.need()) CUDA_TRY(cudaFuncSetAttribute(tkc::topk_rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    const size_t sel_smem = (size_t)4 * 2 * k * sizeof(float) + (size_t)4 * 33 * (d + 1) * sizeof(float);  // lists + per-warp row staging
+    const size_t sel_smem = (size_t)4 * 4 * k * sizeof(float) + (size_t)4 * (d + 4) * sizeof(float);  // 2 lists per warp + its query row
     tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_base, d, qn, dn, k, cand, cand_cnt, run_s, run_i, run_cnt,
                                                                        tq, margin);
     LAUNCH_CHECK("topk_rescore_select");
