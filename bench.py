@@ -300,7 +300,8 @@ def build_tower(env, conf, batches, params, dp_comm, sync_bn=False):
     from dssm_b200 import DSSMTower
     from dssm_b200.parallel import DataParallelTower
 
-    max_nnz = max(b.nnz for b in batches)
+    # 5 % head-room: later legs (dp_parity, the loader's epoch) draw fresh batches whose nnz varies by a fraction of a percent
+    max_nnz = int(max(b.nnz for b in batches) * 1.05) + 1024
     want_symm = env.world > 1 and dp_comm == "nvlink"
     tower = None
     if want_symm:
@@ -499,6 +500,7 @@ def dp_parity(env, args, res, sync_bn=False, multicast=None):
     tower.m.zero_(); tower.v.zero_(); tower.comm.zero_()
     tower.beta_pow.copy_(torch.tensor([conf.beta1, conf.beta2], dtype=torch.float32))
     b = make_batch(conf, seed=7000 + rank)
+    assert b.nnz <= tower.max_nnz, (b.nnz, tower.max_nnz)
     loss_local = dp.train_step(tower.to_device(b)).item()
     torch.cuda.synchronize()
     # replicas bit-identical?
