@@ -4,10 +4,10 @@
 //      [doc tile of 128][k-block of 64][128 rows x 128 B, SWIZZLE_128B]
 // so that a query batch streams 256 B per document (half of the fp32 rows) with one cp.async.bulk per 32 KB tile and no
 // conversion or swizzling at query time.  The filter then is a warp-specialised tcgen05 pipeline:
-//      warp 8   lane 0: bulk copies of doc tiles into a 3-stage ring (mbarrier complete_tx)
-//      warp 9   lane 0: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), TWO resident query tiles (256 queries) per
+//      warp 16  lane 0: bulk copies of doc tiles into a 3-stage ring (mbarrier complete_tx)
+//      warp 17  lane 0: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), TWO resident query tiles (256 queries) per
 //               doc tile, accumulators double-buffered: 2 tiles x 2 buffers x 128 columns = the 512 TMEM columns
-//      warps 0-7  drain TMEM: approx cosine * ||q|| = <q_bf16, d_hat_bf16> against the query's threshold (the doc norm is
+//      warps 0-15 drain TMEM: approx cosine * ||q|| = <q_bf16, d_hat_bf16> against the query's threshold (the doc norm is
 //               already inside d_hat: one compare per score), survivors appended to the query's candidate list
 // |approx - exact| <= 2^-8 (both operands rounded to nearest bf16, Cauchy-Schwarz) < MARGIN_BF16, the threshold is a lower
 // bound of the final k-th best, so no true top-k document is dropped; survivors are re-scored EXACTLY from the fp32 rows
@@ -28,8 +28,11 @@ constexpr int KB = 2;                          // k-blocks of 64 bf16 (= one 128
 constexpr int KBLK_BYTES = 128 * 128;          // [128 rows x 128 B]
 constexpr int TILE_BYTES = KB * KBLK_BYTES;    // 32 KB per 128 x 128 bf16 tile
 constexpr int STAGES = 3;
-constexpr int EPI_THREADS = 256;               // warps 0-7
+constexpr int EPI_WARPS = 16;                  // (TMEM lane quadrant) x (query tile) x (column half of the doc tile)
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + 64;      // + loader warp + MMA warp
+constexpr int RESERVE = 32;                    // candidate slots a thread reserves per atomic (see the epilogue); fewer when a
+                                               // query is split over many CTAs, so the unused tails stay below CAP / 4
 constexpr int CAP = 2048;                      // candidate ids per query per pass (same as topk_tc.cu)
 constexpr float MARGIN_BF16 = 4.5e-3f;         // > 2^-8 + fp32 slack
 
@@ -87,7 +90,8 @@ build_image_kernel(const float* __restrict__ X, int64_t n, int64_t n_pad /* rows
 __global__ void __launch_bounds__(THREADS, 1)
 topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __restrict__ d_img, int64_t doc_lo, int64_t doc_hi,
                         const float* __restrict__ tq /* (tau - margin) * ||q|| */, const float* __restrict__ qn, int id_base,
-                        int2* __restrict__ cand, int* __restrict__ cand_cnt, int* __restrict__ overflow, int tiles_per_split) {
+                        int2* __restrict__ cand, int* __restrict__ cand_cnt, int* __restrict__ overflow, int tiles_per_split,
+                        int reserve /* candidate slots per reservation, <= RESERVE */) {
     extern __shared__ char smem_raw[];
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], q_full;
     __shared__ uint32_t tmem_slot;
@@ -95,7 +99,7 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
     char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     char* q_sm = smem;                                  // QTILES x 32 KB
     char* d_sm = smem + QTILES * TILE_BYTES;            // STAGES x 32 KB
-    float4* stash = reinterpret_cast<float4*>(d_sm + STAGES * TILE_BYTES);  // [EPI_THREADS][8] float4
+    float4* stash = reinterpret_cast<float4*>(d_sm + STAGES * TILE_BYTES);  // [EPI_THREADS][4] float4
 
     // doc tiles are addressed relative to the index (doc_lo is a multiple of DT: caller's contract)
     const int64_t tile_lo = doc_lo / DT;
@@ -124,7 +128,7 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (warp == 8) {
+    if (warp == EPI_WARPS) {
         // ------------------------------------------------------------------ loader
         if (lane == 0) {
             // the query image is padded (with zero rows) to a multiple of QTILES tiles, so both tiles can always be copied
@@ -135,7 +139,7 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
                 bulk_copy_g2s(d_sm + s * TILE_BYTES, d_img + (size_t)(tile_lo + t_begin + t) * TILE_BYTES, (uint32_t)TILE_BYTES, &full[s]);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(QT, DT);
@@ -162,12 +166,45 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 0-7)
-        // warp w: TMEM lanes 32*(w%4).., query tile w/4
-        const int lane_grp = warp & 3, qt = warp >> 2;
+        // ------------------------------------------------------------------ epilogue (warps 0-15)
+        // warp w: TMEM lanes 32*(w%4).., query tile (w/4)%2, columns 64*(w/8).. of the doc tile.  A thread owns ONE query.
+        //
+        // Candidate slots are RESERVED in runs of RESERVE per (thread, CTA) with one atomic, not one atomic per candidate:
+        // a survivor is rare per thread (a few % of the 32-column chunks) but almost every chunk has one somewhere in the
+        // warp, so with an atomic per candidate every warp sat out a full L2 atomic round trip on nearly every chunk --
+        // ncu (profiles/r2_ncu_bf16_filter.txt): 3100 cycles per doc tile against ~1000 of MMA work, tensor pipe 22 %.
+        // Slots of the last run that stay unused are filled with the id -1 the rescoring pass skips.
+        const int lane_grp = warp & 3, qt = (warp >> 2) & 1, half = warp >> 3;
         const int q = (qt0 + qt) * QT + lane_grp * 32 + lane;
         const float t_q = q < nq ? __ldg(tq + q) : INFINITY;
         const float inv_qn = q < nq ? 1.0f / __ldg(qn + q) : 0.f;
+        int res_pos = 0, res_left = 0;
+        float4* row = stash + (size_t)tid * 4;  // 16 scores of this thread (one half chunk)
+        const float* rowf = reinterpret_cast<const float*>(row);
+        auto emit = [&](uint32_t keep16, const uint32_t* r16, int64_t doc_first) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                row[i ^ (lane & 3)] = make_float4(__uint_as_float(r16[4 * i]), __uint_as_float(r16[4 * i + 1]),
+                                                  __uint_as_float(r16[4 * i + 2]), __uint_as_float(r16[4 * i + 3]));
+            while (keep16) {
+                const int j = __ffs(keep16) - 1;
+                keep16 &= keep16 - 1;
+                if (res_left == 0) {
+                    res_pos = atomicAdd(cand_cnt + q, reserve);
+                    res_left = reserve;
+                    if (res_pos + reserve > CAP) {
+                        *overflow = 1;
+                        res_left = res_pos < CAP ? CAP - res_pos : 0;
+                    }
+                }
+                if (res_left > 0) {
+                    const float dot = rowf[(((j >> 2) ^ (lane & 3)) << 2) + (j & 3)];
+                    cand[(size_t)q * CAP + res_pos] = make_int2(id_base + (int)(doc_first + j), __float_as_int(dot * inv_qn));
+                    ++res_pos;
+                    --res_left;
+                }
+            }
+        };
         for (int t = 0; t < n_tiles; ++t) {
             const int b = t & 1;
             mbar_wait(&acc_full[b], (uint32_t)((t >> 1) & 1));
@@ -175,7 +212,8 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
             const int64_t d0 = doc_lo + (int64_t)(t_begin + t) * DT;
             const int nvalid = (int)((doc_hi - d0) < (int64_t)DT ? (doc_hi - d0) : (int64_t)DT);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int ch = half * 2 + c2;
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((qt * 2 + b) * DT + ch * 32), r);
                 uint32_t keep = 0;
@@ -183,29 +221,13 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
                 for (int j = 0; j < 32; ++j) keep |= (__uint_as_float(r[j]) >= t_q ? 1u : 0u) << j;
                 const int col0 = ch * 32;
                 if (nvalid - col0 < 32) keep &= (nvalid - col0 <= 0) ? 0u : (0xffffffffu >> (32 - (nvalid - col0)));  // partial last tile
-                if (keep) {
-                    float4* row = stash + (size_t)tid * 8;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        row[i ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                          __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    const float* rowf = reinterpret_cast<const float*>(row);
-                    while (keep) {
-                        const int j = __ffs(keep) - 1;
-                        keep &= keep - 1;
-                        const int pos = atomicAdd(cand_cnt + q, 1);
-                        if (pos < CAP) {
-                            const float dot = rowf[(((j >> 2) ^ (lane & 7)) << 2) + (j & 3)];
-                            cand[(size_t)q * CAP + pos] = make_int2(id_base + (int)(d0 + col0 + j), __float_as_int(dot * inv_qn));
-                        } else {
-                            *overflow = 1;
-                        }
-                    }
-                }
+                if (keep & 0xffffu) emit(keep & 0xffffu, r, d0 + col0);
+                if (keep >> 16) emit(keep >> 16, r + 16, d0 + col0 + 16);
             }
             tc_fence_before();
             mbar_arrive_cta(&acc_empty[b]);
         }
+        for (; res_left > 0; --res_left, ++res_pos) cand[(size_t)q * CAP + res_pos] = make_int2(-1, __float_as_int(-INFINITY));
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, 512);
@@ -298,7 +320,7 @@ extern "C" int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float*
     const char* d_img = (const char*)index + index_norm_bytes(nd);
     const int nq_pad = (nq + tkb::QT * tkb::QTILES - 1) / (tkb::QT * tkb::QTILES) * (tkb::QT * tkb::QTILES);
     static PerDeviceOnce once;
-    const size_t smem = (size_t)(tkb::QTILES + tkb::STAGES) * tkb::TILE_BYTES + (size_t)tkb::EPI_THREADS * 32 * sizeof(float) + 1024;
+    const size_t smem = (size_t)(tkb::QTILES + tkb::STAGES) * tkb::TILE_BYTES + (size_t)tkb::EPI_THREADS * 16 * sizeof(float) + 1024;
     if (once.need()) CUDA_TRY(cudaFuncSetAttribute(tkb::topk_bf16_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = topk_row_norms(Q, nq, d, w.qn, st);
     if (rc != DSSM_OK) return rc;
@@ -308,13 +330,15 @@ extern "C" int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float*
     CUDA_TRY(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nq_pad * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
     // pass 0: exact top-k of the first `seed` docs (a multiple of the doc tile, so the filter passes start tile-aligned)
-    const int seed = nd < 4096 ? (int)nd : 4096;
+    // 1024 docs: the exact kernels cost ~0.16 us per doc at nq = 4096 (the warp-per-query selection dominates), one more
+    // filter pass costs ~0.2 ms
+    const int seed = nd < 1024 ? (int)nd : 1024;
     rc = topk_exact_chunk(Q, nq, docs, 0, seed, d, w.qn, dn, w.S, seed, id_offset, k, w.run_s, w.run_i, w.run_cnt, st);
     if (rc != DSSM_OK) return rc;
     rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkb::MARGIN_BF16, st);
     if (rc != DSSM_OK) return rc;
     const int n_qgroups = nq_pad / (tkb::QT * tkb::QTILES);
-    int64_t lo = seed, chunk = 4 * (int64_t)4096;
+    int64_t lo = seed, chunk = 4 * (int64_t)seed;
     while (lo < nd) {
         const int64_t hi = (nd - lo <= chunk + chunk / 2) ? nd : lo + chunk;  // fold a short tail into the last pass
         const int tiles = (int)((hi - lo + tkb::DT - 1) / tkb::DT);
@@ -323,8 +347,10 @@ extern "C" int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float*
         if (splits > tiles) splits = tiles;
         const int tps = (tiles + splits - 1) / splits;
         dim3 grid(n_qgroups, (tiles + tps - 1) / tps);
+        int reserve = tkb::CAP / (4 * (int)grid.y);
+        reserve = reserve > tkb::RESERVE ? tkb::RESERVE : (reserve < 1 ? 1 : reserve);
         tkb::topk_bf16_filter_kernel<<<grid, tkb::THREADS, smem, st>>>(w.q_img, nq, d_img, lo, hi, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
-                                                                       w.overflow, tps);
+                                                                       w.overflow, tps, reserve);
         LAUNCH_CHECK("topk_bf16_filter");
         rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkb::MARGIN_BF16, st);
         if (rc != DSSM_OK) return rc;

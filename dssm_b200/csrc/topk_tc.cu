@@ -33,7 +33,7 @@ constexpr int TILE_BYTES = QT * DIM * 4;     // 64 KB
 constexpr int KBLK_BYTES = QT * 128;         // one [128 rows x 32 floats] block
 constexpr int CAP = 2048;                    // candidate ids per query per pass
 constexpr float MARGIN = 2.5e-3f;            // > 2^-9 (tf32 truncation of both operands) + fp32 slack
-constexpr int SEED_DOCS = 4096;              // exact pass that seeds the thresholds; later passes grow x4
+constexpr int SEED_DOCS = 1024;              // exact pass that seeds the thresholds (0.16 us per doc at nq = 4096); later passes grow x4
 
 // stage one [128 x 128] fp32 tile (rows row0.. of X, `rows_valid` of them real) into SW128 K-major blocks with cp.async.
 // Chunk i of a thread always goes to the same place of the tile: 16-byte chunk id = tid + 256*i  ->  row id/32,
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ docs, int64_t doc_lo, int64_t doc_hi,
                       const float* __restrict__ dn, const float* __restrict__ tq /* (tau - margin) * ||q|| */,
                       const float* __restrict__ qn, int id_base /* id of doc row 0 */, int2* __restrict__ cand, int* __restrict__ cand_cnt,
-                      int* __restrict__ overflow, int tiles_per_split) {
+                      int* __restrict__ overflow, int tiles_per_split, int reserve /* candidate slots per reservation */) {
     extern __shared__ char smem_raw[];
     __shared__ uint64_t mma_done[2];
     __shared__ uint32_t tmem_slot;
@@ -111,6 +111,11 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
     const float t_q = q < nq ? __ldg(tq + q) : INFINITY;
     const float inv_qn = q < nq ? 1.0f / __ldg(qn + q) : 0.f;
 
+    // Candidate slots are reserved in runs of `reserve` per (thread, CTA) -- one atomic per run, not per candidate: a
+    // survivor is rare per thread but nearly every chunk has one somewhere in the warp, and every lane of the warp then
+    // waited out the atomic's L2 round trip (see topk_bf16.cu).  Unused slots of the last run get the id -1 (skipped by
+    // the rescoring pass).
+    int res_pos = 0, res_left = 0;
     // drain the accumulator of this CTA's tile number `tr` (relative index): approx dot -> threshold test -> append
     auto wait_mma = [&](int tr) {
         mbar_wait(&mma_done[tr & 1], (uint32_t)((tr >> 1) & 1));
@@ -150,14 +155,21 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
                 while (keep) {
                     const int j = __ffs(keep) - 1;
                     keep &= keep - 1;
-                    const int pos = atomicAdd(cand_cnt + q, 1);
-                    if (pos < CAP) {
+                    if (res_left == 0) {
+                        res_pos = atomicAdd(cand_cnt + q, reserve);
+                        res_left = reserve;
+                        if (res_pos + reserve > CAP) {
+                            *overflow = 1;
+                            res_left = res_pos < CAP ? CAP - res_pos : 0;
+                        }
+                    }
+                    if (res_left > 0) {
                         // id + the approximate cosine (the rescoring pass skips candidates that can no longer enter the list)
                         const float dot = rowf[(((j >> 2) ^ (lane & 7)) << 2) + (j & 3)];
                         const float nd = s_dn[tr % 3][col0 + j];
-                        cand[(size_t)q * CAP + pos] = make_int2(id_base + (int)(d0 + col0 + j), __float_as_int(dot * inv_qn / nd));
-                    } else {
-                        *overflow = 1;
+                        cand[(size_t)q * CAP + res_pos] = make_int2(id_base + (int)(d0 + col0 + j), __float_as_int(dot * inv_qn / nd));
+                        ++res_pos;
+                        --res_left;
                     }
                 }
             }
@@ -198,6 +210,7 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
     }
     wait_mma(t_end - 1 - t_begin);
     drain(t_end - 1 - t_begin);  // last tile
+    for (; res_left > 0; --res_left, ++res_pos) cand[(size_t)q * CAP + res_pos] = make_int2(-1, __float_as_int(-INFINITY));
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
@@ -242,7 +255,8 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
             const int2 c2 = cand[(size_t)q * CAP + base + lane];
             cid0 = c2.x;
             const float approx = __int_as_float(c2.y);
-            alive = (cnt < k) || !(approx + margin < ls[k - 1]);  // NaN approx (zero-norm doc) stays alive
+            // id -1: an unused slot of a filter thread's reserved run (topk_bf16.cu); NaN approx (zero-norm doc) stays alive
+            alive = cid0 >= 0 && ((cnt < k) || !(approx + margin < ls[k - 1]));
         }
         const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
         const int na = __popc(alive_mask);
@@ -390,8 +404,10 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
         if (splits > tiles) splits = tiles;
         const int tps = (tiles + splits - 1) / splits;
         dim3 grid(n_qtiles, (tiles + tps - 1) / tps);
+        int reserve = tkc::CAP / (4 * (int)grid.y);  // unused tails of the reserved runs stay below CAP / 4 per query
+        reserve = reserve > 32 ? 32 : (reserve < 1 ? 1 : reserve);
         tkc::topk_tc_filter_kernel<<<grid, tkc::THREADS, smem, st>>>(Q, nq, docs, lo, hi, w.dn, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
-                                                                     w.overflow, tps);
+                                                                     w.overflow, tps, reserve);
         LAUNCH_CHECK("topk_tc_filter");
         rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
         if (rc != DSSM_OK) return rc;
