@@ -79,6 +79,7 @@ SIGNATURES = {
     "dssm_peer_signal": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "dssm_peer_wait": (C.c_int, [_p, _i32, _i32, _i32, _p]),
     "dssm_peer_epoch_advance": (C.c_int, [_p, _p]),
+    "dssm_peer_barrier": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dssm_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "dssm_bn_forward": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "dssm_bn_act_apply": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),

@@ -278,24 +278,27 @@ class DataParallelTower:
 
         t, c, n = self.tower, self.tower.conf, self.world
         main = torch.cuda.current_stream(t.device)
-        own_flags = ptr(self._flag_buf)
         t.fwd_bwd_begin_staged()
-        w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        # [grads beyond W1 | EMA shadows]: 0.5 MB, stays on NCCL.  Its all-reduce AND the Adam step on it run on the exchange
+        # stream beside the gather / owner pass (they share nothing with W1; the beta powers are only read until
+        # adam_advance) -- on the main stream they were ~10 us of serial tail per step.
+        self._xstream.wait_stream(main)
+        with torch.cuda.stream(self._xstream):
+            w_rest = dist.all_reduce(t.comm[self.w1_end:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            w_rest.wait()
+            t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
         check(lib.dssm_tower_backward_w1_push(t._h, self._peer_slots, self._peer_valid, self._epoch_ptr, n, self.rank, self._per,
                                               stream_ptr(main)))
-        check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, 0, 2, stream_ptr(main)))
-        check(lib.dssm_peer_wait(own_flags, n, 0, 2, stream_ptr(main)))  # every rank's rows for my shard have landed
+        # every rank's rows for my shard have landed (signal + wait in one launch)
+        check(lib.dssm_peer_barrier(self._peer_flags, n, self.rank, 0, 2, 0, stream_ptr(main)))
         check(lib.dssm_w1_slots_reduce_adam(ptr(self._slots), ptr(self._valid), self._epoch_ptr, self._peer_w,
                                             self._mc_w if self.use_multicast else None, n, self.rank, c.TRIGRAM_D, c.layers[0], self._per,
                                             ptr(t.m), ptr(t.v), ptr(t.beta_pow), c.learning_rate, c.beta1, c.beta2, c.adam_eps,
                                             stream_ptr(main)))
-        w_rest.wait()
-        t.adam_range(self.w1_end, t.P - self.w1_end, 1.0)
+        main.wait_stream(self._xstream)
         t.adam_advance()
-        # every owner's rows have landed in every replica of W1 before anybody's next forward reads it
-        check(lib.dssm_peer_signal(self._peer_flags, n, self.rank, 1, 2, stream_ptr(main)))
-        check(lib.dssm_peer_wait(own_flags, n, 1, 2, stream_ptr(main)))
-        check(lib.dssm_peer_epoch_advance(own_flags, stream_ptr(main)))
+        # every owner's rows have landed in every replica of W1 before anybody's next forward reads it; ends the step (epoch)
+        check(lib.dssm_peer_barrier(self._peer_flags, n, self.rank, 1, 2, 1, stream_ptr(main)))
 
     def _step_staged_nvlink(self) -> None:
         """forward + dense backward + CSC (one C call / graph), then the dW1 gather in x_chunks column chunks on the main

@@ -172,6 +172,11 @@ size_t dssm_peer_flags_bytes(void);
 int dssm_peer_signal(void* const* host_peer_flags, int32_t n_ranks, int32_t self, int32_t idx, int32_t stride, dssm_stream_t stream);
 int dssm_peer_wait(const void* own_flags, int32_t n_ranks, int32_t idx, int32_t stride, dssm_stream_t stream);
 int dssm_peer_epoch_advance(void* own_flags, dssm_stream_t stream);
+/* dssm_peer_signal(idx) followed by dssm_peer_wait(idx) in ONE launch (a full cross-rank barrier on `stream`); with
+ * advance_epoch != 0 it also does the dssm_peer_epoch_advance that ends a step.  Used by the push exchange, whose two sync
+ * points sit on the critical path of every data-parallel step. */
+int dssm_peer_barrier(void* const* host_peer_flags, int32_t n_ranks, int32_t self, int32_t idx, int32_t stride, int32_t advance_epoch,
+                      dssm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * batch_normalization(x, phase_train, out_size)  (new_dssm.py:62-88), both instances of one layer
