@@ -282,50 +282,45 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     mbar_wait(&done_bar, 0);
     tc_fence_after();
 
-    // ---- epilogue: TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
+    // ---- epilogue: TMEM -> registers -> shared-memory tile -> (+bias) -> global, full rows per warp (coalesced; see the
+    // warp-specialised kernel below for the measurement).  Warp w owns TMEM lanes 32*(w%4)..+31; the pipeline stages are
+    // free once done_bar has completed.
     const int lane_grp = warp & 3;
-    const int row = m0 + lane_grp * 32 + lane;
     const int nchunks = BN / 32;  // BN is a multiple of 32 on this path
     const int nacc = nkb < nacc_used ? nkb : nacc_used;
+    float* tile = reinterpret_cast<float*>(smem);
+    const int ld = BN + 4;
     for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;  // +0.0f
         for (int a = 0; a < nacc; ++a) {
             uint32_t t[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
-                  "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]),
-                  "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]),
-                  "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
         }
-        if (row < g.M) {
-            const int nb = n0 + ch * 32;
-            float* out = g.D + (MN ? (size_t)blockIdx.z * g.M * g.N : 0) + (size_t)row * g.N + nb;
+        float* dst = tile + (size_t)(lane_grp * 32 + lane) * ld + ch * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (nb + j + 3 < g.N) {
-                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
-                    if (g.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    *reinterpret_cast<float4*>(out + j) = o;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (nb + j + q < g.N) out[j + q] = __uint_as_float(r[j + q]) + (g.bias ? __ldg(g.bias + nb + j + q) : 0.f);
-                }
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                              __uint_as_float(r[j + 3]));
+    }
+    tc_fence_before();
+    __syncthreads();
+    {
+        float* Dz = g.D + (MN ? (size_t)blockIdx.z * g.M * g.N : 0);
+        const int n4 = BN / 4;
+        const int nvalid = min(BN, g.N - n0);  // N is a multiple of 4 on this path
+        for (int c4 = lane; c4 < n4; c4 += 32) {
+            if (c4 * 4 >= nvalid) continue;
+            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) bz = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c4 * 4));
+            for (int rr = warp; rr < BM; rr += THREADS / 32) {
+                if (m0 + rr >= g.M) break;
+                float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c4 * 4);
+                o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
+                *reinterpret_cast<float4*>(Dz + (size_t)(m0 + rr) * g.N + n0 + c4 * 4) = o;
             }
         }
     }
@@ -381,6 +376,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
     const int nkb = (g.K + BK - 1) / BK;
     const int kpad = nkb * BK;
 
+    // Producers (warps 0-7): loop-invariant addressing, and the first WS_PF k-blocks of activation loads go out BEFORE the
+    // CTA's setup (TMEM allocation, barrier init, scale/shift to shared memory): their L2 round trip (~2-3 us when all
+    // CTAs of the launch pull at once) then overlaps the ~1.2 us of setup instead of following it.
+    // chunk i of a producer thread: tile row r_i = (tid + 256 i) / 8, 16-byte chunk c = tid % 8
+    const int c = tid & 7;
+    const float* rowp[4];
+    uint32_t off[4];
+    bool okm[4];
+    int seg[4];
+    // register ring, WS_PF k-blocks of loads in flight per thread (64 KB per CTA): one k-block ahead leaves most of
+    // the L2 round trip exposed, because converting a k-block takes far less time than fetching one
+    float4 buf[WS_PF][4];
+    auto load4 = [&](int kb, float4 (&q)[4]) {
+        const bool okk = kb < nkb && kb * BK + c * 4 < g.K;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            q[i] = (okm[i] && okk) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (warp < 8) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = (tid >> 3) + 32 * i;
+            const int m = m0 + r;
+            okm[i] = m < g.M;
+            seg[i] = m < g.Bseg ? 0 : 1;
+            rowp[i] = g.A + (size_t)(okm[i] ? m : 0) * g.K + c * 4;
+            off[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < WS_PF; ++j) load4(j, buf[j]);
+    }
+
     if (warp == 0) tmem_alloc(&tmem_base_slot, TMEM_COLS);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -404,32 +431,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
 
     if (warp < 8) {
         // ------------------------------------------------------------------ producers (256 threads, 4 chunks each)
-        // chunk i of this thread: tile row r_i = (tid + 256 i) / 8, 16-byte chunk c = tid % 8 -- all loop-invariant
-        const int c = tid & 7;
-        const float* rowp[4];
-        uint32_t off[4];
-        bool okm[4];
-        int seg[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = (tid >> 3) + 32 * i;
-            const int m = m0 + r;
-            okm[i] = m < g.M;
-            seg[i] = m < g.Bseg ? 0 : 1;
-            rowp[i] = g.A + (size_t)(okm[i] ? m : 0) * g.K + c * 4;
-            off[i] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-        }
-        // register ring, WS_PF k-blocks of loads in flight per thread (64 KB per CTA): one k-block ahead leaves most of
-        // the L2 round trip exposed, because converting a k-block takes far less time than fetching one
-        float4 buf[WS_PF][4];
-        auto load4 = [&](int kb, float4 (&q)[4]) {
-            const bool okk = kb < nkb && kb * BK + c * 4 < g.K;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                q[i] = (okm[i] && okk) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-#pragma unroll
-        for (int j = 0; j < WS_PF; ++j) load4(j, buf[j]);
         for (int kb0 = 0; kb0 < nkb; kb0 += WS_PF) {
 #pragma unroll
             for (int j = 0; j < WS_PF; ++j) {
@@ -518,6 +519,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
         float* sc_n = reinterpret_cast<float*>(smem);
         float* sc_mu = sc_n + 4 * MAX_BN;
         float* sc_m2 = sc_mu + 4 * MAX_BN;
+        if (!g.fbn.on) {
+            // Coalesced epilogue: TMEM -> registers -> the (now free) pipeline shared memory as a [128][BN + 4] fp32 tile ->
+            // full rows to global, a warp writing 512 contiguous bytes per instruction.  Writing straight from the TMEM
+            // layout (a lane = a row) made every 128-bit store instruction touch 32 different rows, 16 bytes each: ~2 us per
+            // 32-column chunk (measured with in-kernel timestamps: 4.1 us of a 17 us tile at BN = 128).
+            float* tile = reinterpret_cast<float*>(smem);
+            const int ld = BN + 4;
+            for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
+                for (int a = 1; a < nacc_e; ++a) {
+                    uint32_t t[32];
+                    tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+                }
+                float* dst = tile + (size_t)(lane_grp * 32 + lane) * ld + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                                      __uint_as_float(r[j + 3]));
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+            const int n4 = BN / 4;                          // float4 columns of the tile (BN is a multiple of 32)
+            const int nvalid = min(BN, g.N - n0);           // N is a multiple of 4 on this path
+            for (int c4 = lane; c4 < n4; c4 += 32) {
+                if (c4 * 4 >= nvalid) continue;
+                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) bz = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c4 * 4));
+                for (int rr = warp; rr < BM; rr += 8) {
+                    if (m0 + rr >= g.M) break;
+                    float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c4 * 4);
+                    o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
+                    *reinterpret_cast<float4*>(g.D + (size_t)(m0 + rr) * g.N + n0 + c4 * 4) = o;
+                }
+            }
+        } else
         for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);

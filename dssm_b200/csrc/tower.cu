@@ -145,6 +145,8 @@ struct dssm_tower {
     //        off `side` right after csc_hist and no longer queues behind the scans / fill / row sort (or they behind it);
     // side3: the dW GEMMs of the dense backward (independent of the dX chain once dh_l exists), joined before Adam.
     cudaStream_t side2, side3;
+    // capture stream of the whole-step graphs (most urgent priority; see dssm_tower_bind)
+    cudaStream_t main_hi;
     cudaEvent_t ev_hist, ev_join2, ev_dh, ev_join3;
     bool absent_forked, dw_forked;
     // pipelined host feed (dssm_tower_train_step_host_async): upload buffers k%2 filled on the copy stream
@@ -308,6 +310,7 @@ extern "C" int dssm_tower_create(const dssm_config* cfg, dssm_tower** out) {
     t->launches_per_dp = 0;
     t->side = nullptr;
     t->side2 = t->side3 = nullptr;
+    t->main_hi = nullptr;
     t->ev_hist = t->ev_join2 = t->ev_dh = t->ev_join3 = nullptr;
     t->absent_forked = t->dw_forked = false;
     t->copy = nullptr;
@@ -340,6 +343,7 @@ extern "C" void dssm_tower_destroy(dssm_tower* t) {
     if (t->side) cudaStreamDestroy(t->side);
     if (t->side2) cudaStreamDestroy(t->side2);
     if (t->side3) cudaStreamDestroy(t->side3);
+    if (t->main_hi) cudaStreamDestroy(t->main_hi);
     for (cudaEvent_t e : {t->ev_hist, t->ev_join2, t->ev_dh, t->ev_join3})
         if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) {
@@ -363,6 +367,7 @@ extern "C" size_t dssm_tower_workspace_bytes(const dssm_tower* t, int64_t max_nn
     tmp.graph_dp_exec = nullptr;
     tmp.side = nullptr;
     tmp.side2 = tmp.side3 = nullptr;
+    tmp.main_hi = nullptr;
     tmp.ev_hist = tmp.ev_join2 = tmp.ev_dh = tmp.ev_join3 = nullptr;
     tmp.ev_fork = nullptr;
     tmp.ev_join = nullptr;
@@ -418,9 +423,20 @@ extern "C" int dssm_tower_bind(dssm_tower* t, float* params, float* grads, float
     CUDA_TRY(cudaMemset(t->fbn_ws, 0, 256));
     CUDA_TRY(cudaMemset(t->dw_ws, 0, t->dw_ws_bytes));
     if (!t->side) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&t->side3, cudaStreamNonBlocking));
+        // Priorities: the side streams carry work with slack (CSC build, absent-row Adam, dW GEMMs -- consumed only at the end
+        // of the step), the main chain has none.  Side streams get the LEAST urgent priority and the step is captured on an
+        // internal stream of the MOST urgent one (graph kernel nodes inherit the capturing stream's priority), so the block
+        // scheduler places main-chain CTAs first whenever both have blocks pending.  Without it a dW GEMM (144 CTAs, one per
+        // SM) launched beside the dX GEMM of the same layer held the SMs for its whole life and the dX GEMM on the critical
+        // path ran after it (fc_dx3: 23 us inside the step, 12 alone).  DSSM_SIDE_PRIORITY=0: one priority for all (A/B runs).
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // lo = numerically greatest = least urgent
+        const char* sp = getenv("DSSM_SIDE_PRIORITY");
+        if (sp && sp[0] == '0') prio_hi = prio_lo;
+        CUDA_TRY(cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, prio_lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&t->side2, cudaStreamNonBlocking, prio_lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&t->side3, cudaStreamNonBlocking, prio_lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&t->main_hi, cudaStreamNonBlocking, prio_hi));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_hist, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join2, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t->ev_dh, cudaEventDisableTiming));
@@ -628,6 +644,16 @@ static void w1_chunk_cols(const dssm_tower* t, int chunk, int n_chunks, int* c0,
 static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) {
     const dssm_config& c = t->cfg;
     const int n = t->n_layers, R = t->R, B = t->B;
+    // dW GEMMs whose launch is deferred to the start of the dW1 gather (see fork_dw below)
+    int late_dw[DSSM_MAX_LAYERS + 1], n_late = 0;
+    const bool dw_late = getenv("DSSM_DW_LATE") != nullptr;
+    auto launch_dw = [&](int l, dssm_stream_t st_dw) -> int {
+        const std::string ls = std::to_string(l);
+        const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
+        const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
+        return dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
+                              c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, st_dw);
+    };
     for (int l = n; l >= 1; --l) {
         const std::string ls = std::to_string(l);
         if (c.use_bn && t->sync_n > 1) {
@@ -653,18 +679,27 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
             const float* sc = c.use_bn ? t->bn_scale[l - 1] : nullptr;
             const float* sh = c.use_bn ? t->bn_shift[l - 1] : nullptr;
             // under BN the bias gradient came out of dssm_bn_act_backward; without BN it is the column sum of dH
-            // dW_l needs dh_l and h_{l-1} only: under BN (no colsum sharing its workspace) it runs on side3 beside the dX chain
-            const bool fork_dw = c.use_bn && !(g_timer && g_timer->on) && getenv("DSSM_NO_DW_FORK") == nullptr;
+            // dW_l needs dh_l and h_{l-1} only: under BN (no colsum sharing its workspace) it runs on side3 beside the dX chain.
+            // The dX GEMM -- the one on the critical path -- is issued FIRST, so its CTAs get the SMs first.
+            // (the in-graph %globaltimer timeline keeps the fork: its stamps sit between the main-stream calls only)
+            const bool fork_dw = c.use_bn && !(g_timer && g_timer->on && !g_timer->stamps) && getenv("DSSM_NO_DW_FORK") == nullptr;
             dssm_stream_t dw_st = s;
-            if (fork_dw) {
+            if (fork_dw && !dw_late) {
                 CUDA_TRY(cudaEventRecord(t->ev_dh, (cudaStream_t)s));
                 CUDA_TRY(cudaStreamWaitEvent(t->side3, t->ev_dh, 0));
                 dw_st = (dssm_stream_t)t->side3;
                 t->dw_forked = true;
             }
-            TRY(dssm_fc_bwd_dw(t->h[l - 1], R, t->L[l - 1], B, sc, sh, c.act, t->dh[l], t->L[l], t->G_("W" + ls),
-                               c.use_bn ? nullptr : t->G_("b" + ls), c.gemm_mode, t->dw_ws, t->dw_ws_bytes, dw_st));
-            markf("fc_dw" + ls);
+            auto issue_dw = [&]() -> int {
+                if (fork_dw && dw_late) {  // launched on side3 when the dX chain is through (beside the dW1 gather)
+                    late_dw[n_late++] = l;
+                    return DSSM_OK;
+                }
+                TRY(launch_dw(l, dw_st));
+                if (!fork_dw) markf("fc_dw" + ls);
+                return DSSM_OK;
+            };
+            if (!fork_dw) TRY(issue_dw());  // same stream: dW first (the profiled timeline keeps its order)
             if (is_tc_mode(c.gemm_mode) && t->img_dx[l] && t->L[l] % 4 == 0 && t->L[l - 1] % 4 == 0) {
                 TRY(dssm_fc_bwd_dx_tc_img(t->dh[l], R, t->L[l], t->img_dx[l], t->L[l - 1], t->dh[l - 1], tc_passes_of(c.gemm_mode), s));
             } else {
@@ -672,8 +707,15 @@ static int tower_backward_impl(dssm_tower* t, dssm_stream_t s, int w1_mode = 0) 
                                    t->fc_ws_bytes, s));
             }
             markf("fc_dx" + ls);
+            if (fork_dw) TRY(issue_dw());
         } else {
             mark(PH_DENSE_BWD);
+            if (n_late > 0) {
+                CUDA_TRY(cudaEventRecord(t->ev_dh, (cudaStream_t)s));
+                CUDA_TRY(cudaStreamWaitEvent(t->side3, t->ev_dh, 0));
+                for (int i = 0; i < n_late; ++i) TRY(launch_dw(late_dw[i], (dssm_stream_t)t->side3));
+                t->dw_forked = true;
+            }
             if (t->csc_forked) {  // join: the CSC built beside the forward is ready (or will be) -- gather only
                 CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join, 0));
                 if (t->absent_forked) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)s, t->ev_join2, 0));
@@ -862,8 +904,11 @@ extern "C" int dssm_tower_capture_graph(dssm_tower* t, dssm_stream_t stream) {
     if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
     if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
     const int64_t before = g_launch_count;
+    // captured on the tower's own most-urgent-priority stream (nothing executes during capture; the graph is launched on
+    // the caller's stream): the main chain's kernel nodes outrank the side streams' (see dssm_tower_bind)
+    st = t->main_hi;
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
+    const int rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, (dssm_stream_t)st);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc != DSSM_OK) {
@@ -885,9 +930,10 @@ extern "C" int dssm_tower_capture_graph_dp(dssm_tower* t, dssm_stream_t stream) 
     if (t->graph_dp_exec) { cudaGraphExecDestroy(t->graph_dp_exec); t->graph_dp_exec = nullptr; }
     if (t->graph_dp) { cudaGraphDestroy(t->graph_dp); t->graph_dp = nullptr; }
     const int64_t before = g_launch_count;
+    st = t->main_hi;  // as in dssm_tower_capture_graph
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = tower_forward_impl(t, t->st_indptr, t->st_indices, t->st_values, 1, 1, true, stream);
-    if (rc == DSSM_OK) rc = tower_backward_impl(t, stream, 1);
+    int rc = tower_forward_impl(t, t->st_indptr, t->st_indices, t->st_values, 1, 1, true, (dssm_stream_t)st);
+    if (rc == DSSM_OK) rc = tower_backward_impl(t, (dssm_stream_t)st, 1);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &g);
     t->fwd_train_done = false;
@@ -1081,7 +1127,8 @@ extern "C" int dssm_tower_profile_timeline(dssm_tower* t, char* names, int32_t n
     CUDA_TRY(cudaMalloc(&d_stamps, MAX_STAMPS * sizeof(unsigned long long)));
     std::vector<std::string> nm;
     PhaseTimer pt;
-    pt.st = st;
+    cudaStream_t cap = t->main_hi;  // captured like the real step (dssm_tower_capture_graph), launched on the caller's stream
+    pt.st = cap;
     pt.on = true;
     pt.serial = false;
     pt.fine_ev = nullptr;
@@ -1090,13 +1137,13 @@ extern "C" int dssm_tower_profile_timeline(dssm_tower* t, char* names, int32_t n
     cudaGraph_t g = nullptr;
     cudaGraphExec_t ge = nullptr;
     int rc = DSSM_OK;
-    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
         g_timer = &pt;
-        rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, stream);
+        rc = tower_step_impl(t, t->st_indptr, t->st_indices, t->st_values, (dssm_stream_t)cap);
         if (rc == DSSM_OK) markf("adam_rest");
         g_timer = nullptr;
-        e = cudaStreamEndCapture(st, &g);
+        e = cudaStreamEndCapture(cap, &g);
     }
     if (rc == DSSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ge, g, 0);
     for (int i = 0; rc == DSSM_OK && e == cudaSuccess && i < 3; ++i) e = cudaGraphLaunch(ge, st);

@@ -365,7 +365,8 @@ class DataParallelTower:
             return
         t = self.tower
         try:
-            s = torch.cuda.Stream(device=t.device)
+            # most urgent priority: the main chain's kernel nodes then outrank the tower's side streams (csrc/tower.cu: bind)
+            s = torch.cuda.Stream(device=t.device, priority=-1 if os.environ.get("DSSM_SIDE_PRIORITY") != "0" else 0)
             s.wait_stream(torch.cuda.current_stream(t.device))
             with torch.cuda.stream(s):
                 for _ in range(warmup):  # communicators, attribute calls, allocator warm-up outside the capture
