@@ -241,6 +241,8 @@ int topk_exact_chunk(const float* Q, int nq, const float* docs, int64_t doc0, in
                      int ldS, int id0, int k, float* run_s, int* run_i, int* run_cnt, cudaStream_t st);
 int topk_rescore_select(const float* Q, int nq, const float* docs, int id_base, int d, const float* qn, const float* dn, int k,
                         const int2* cand, int* cand_cnt, float* run_s, int* run_i, int* run_cnt, float* tq, float margin, cudaStream_t st);
+int topk_approx_select(int nq, int k, int2* cand, int* cand_cnt, const float* dn, int id_base, const float* qn, float* tq, float margin,
+                       cudaStream_t st);
 
 }  // namespace dssm
 
@@ -329,16 +331,14 @@ extern "C" int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float*
     CUDA_TRY(cudaMemsetAsync(w.run_cnt, 0, (size_t)nq_pad * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nq_pad * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
-    // pass 0: exact top-k of the first `seed` docs (a multiple of the doc tile, so the filter passes start tile-aligned)
-    // 1024 docs: the exact kernels cost ~0.16 us per doc at nq = 4096 (the warp-per-query selection dominates), one more
-    // filter pass costs ~0.2 ms
-    const int seed = nd < 1024 ? (int)nd : 1024;
-    rc = topk_exact_chunk(Q, nq, docs, 0, seed, d, w.qn, dn, w.S, seed, id_offset, k, w.run_s, w.run_i, w.run_cnt, st);
-    if (rc != DSSM_OK) return rc;
-    rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkb::MARGIN_BF16, st);
+    // thresholds start at -inf (empty bags): the first, short pass lets every doc through and seeds the bound; between the
+    // passes topk_approx_select_kernel (topk_tc.cu) raises the thresholds from the APPROXIMATE scores and keeps, per query,
+    // the bag of docs that can still be in the exact top-k; the bag is re-scored exactly once, at the end
+    rc = topk_approx_select(nq, k, w.cand, w.cand_cnt, dn, id_offset, w.qn, w.tq, tkb::MARGIN_BF16, st);
     if (rc != DSSM_OK) return rc;
     const int n_qgroups = nq_pad / (tkb::QT * tkb::QTILES);
-    int64_t lo = seed, chunk = 4 * (int64_t)seed;
+    const int growth = k <= 160 ? 4 : 2;  // candidates per pass ~ growth * k on top of the bag: keep them inside CAP
+    int64_t lo = 0, chunk = 1024;
     while (lo < nd) {
         const int64_t hi = (nd - lo <= chunk + chunk / 2) ? nd : lo + chunk;  // fold a short tail into the last pass
         const int tiles = (int)((hi - lo + tkb::DT - 1) / tkb::DT);
@@ -347,16 +347,18 @@ extern "C" int dssm_corpus_topk_indexed(const float* Q, int32_t nq, const float*
         if (splits > tiles) splits = tiles;
         const int tps = (tiles + splits - 1) / splits;
         dim3 grid(n_qgroups, (tiles + tps - 1) / tps);
-        int reserve = tkb::CAP / (4 * (int)grid.y);
+        int reserve = tkb::CAP / (8 * (int)grid.y);  // unused tails of the reserved runs stay below CAP / 8 per query
         reserve = reserve > tkb::RESERVE ? tkb::RESERVE : (reserve < 1 ? 1 : reserve);
         tkb::topk_bf16_filter_kernel<<<grid, tkb::THREADS, smem, st>>>(w.q_img, nq, d_img, lo, hi, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
                                                                        w.overflow, tps, reserve);
         LAUNCH_CHECK("topk_bf16_filter");
-        rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkb::MARGIN_BF16, st);
+        rc = topk_approx_select(nq, k, w.cand, w.cand_cnt, dn, id_offset, w.qn, w.tq, tkb::MARGIN_BF16, st);
         if (rc != DSSM_OK) return rc;
         lo = hi;
-        chunk *= 4;
+        chunk *= growth;
     }
+    rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkb::MARGIN_BF16, st);
+    if (rc != DSSM_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_scores, w.run_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(out_ids, w.run_i, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(overflow_flag, w.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));

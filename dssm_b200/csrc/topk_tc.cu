@@ -33,7 +33,7 @@ constexpr int TILE_BYTES = QT * DIM * 4;     // 64 KB
 constexpr int KBLK_BYTES = QT * 128;         // one [128 rows x 32 floats] block
 constexpr int CAP = 2048;                    // candidate ids per query per pass
 constexpr float MARGIN = 2.5e-3f;            // > 2^-9 (tf32 truncation of both operands) + fp32 slack
-constexpr int SEED_DOCS = 1024;              // exact pass that seeds the thresholds (0.16 us per doc at nq = 4096); later passes grow x4
+constexpr int SEED_DOCS = 1024;              // docs of the first filter pass (thresholds still -inf: all of them become candidates)
 
 // stage one [128 x 128] fp32 tile (rows row0.. of X, `rows_valid` of them real) into SW128 K-major blocks with cp.async.
 // Chunk i of a thread always goes to the same place of the tile: 16-byte chunk id = tid + 256*i  ->  row id/32,
@@ -309,6 +309,126 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Between two filter passes: new thresholds from the APPROXIMATE scores, no row fetches.  cand[q][0 .. cand_cnt[q]) holds
+// the query's "bag" (survivors of earlier selections) followed by the candidates the last filter pass appended.  One warp
+// per query:
+//   key      monotone uint image of the approximate cosine; 0 = not usable for the bound (unused reserved slot, NaN, doc of
+//            zero norm -- its exact cosine is NaN = -inf whatever the filter computed)
+//   tau      a lower bound of the k-th largest usable approximate cosine: 3 rounds of an 8-bit radix select, i.e. the lower
+//            edge of the 24-bit key bucket that holds the k-th largest (-inf while fewer than k usable entries exist)
+//   bound    k docs have exact >= approx - m >= tau - m, so the FINAL exact k-th best is >= tau - m, so any doc of the final
+//            top-k has approx >= exact - m >= tau - 2m: the bag keeps exactly the entries with approx >= tau - 2m (all of
+//            them while tau = -inf) and the next filter pass keeps docs with dot >= (tau - 2m) * ||q|| * ||d||.
+// tau only rises, so an entry dropped here can never qualify again; after the last pass the bag (k plus the docs within
+// 2m of the k-th best) is re-scored exactly ONCE by topk_rescore_select_kernel.  (Round 2 first version re-scored the
+// ~4k candidates of EVERY pass exactly: ~2500 random 512-byte row fetches per query, 1.1 of the 3.0 ms at C5.)
+__device__ __forceinline__ uint32_t key_of(float a) {
+    const uint32_t u = __float_as_uint(a);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float float_of_key(uint32_t key) {
+    const uint32_t u = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(128)
+topk_approx_select_kernel(int nq, int k, int2* __restrict__ cand, int* __restrict__ cand_cnt, const float* __restrict__ dn, int id_base,
+                          const float* __restrict__ qn, float* __restrict__ tq, float margin2) {
+    extern __shared__ uint32_t sel_sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 4 + w;
+    if (q >= nq) return;
+    uint32_t* keys = sel_sm + (size_t)w * CAP;
+    int* hist = reinterpret_cast<int*>(sel_sm + (size_t)4 * CAP) + w * 256;
+    int2* mine = cand + (size_t)q * CAP;
+    const int n = min(cand_cnt[q], CAP);
+    int usable = 0;
+    for (int i = lane; i < n; i += 32) {
+        const int2 c = mine[i];
+        uint32_t key = 0;
+        if (c.x >= 0) {
+            const float a = __int_as_float(c.y);
+            if (a == a && __ldg(dn + (c.x - id_base)) > 0.f) key = key_of(a);
+        }
+        keys[i] = key;
+        usable += key != 0 ? 1 : 0;
+    }
+    usable = __reduce_add_sync(0xffffffffu, usable);
+    __syncwarp();
+    float tau = -INFINITY;
+    uint32_t thr_key = 0;  // keep every entry with a real id
+    // A query of zero norm has NaN (= -inf) scores everywhere: its top-k is the k lowest ids.  The first pass (thresholds
+    // -inf) covers docs [0, 1024) -- at least the first k -- so keep exactly those and close the threshold (+inf).
+    const float nqv = qn[q];
+    const bool dead_query = !(nqv > 0.f);
+    if (!dead_query && usable >= k) {
+        uint32_t prefix = 0;
+        int want = k;  // rank (from the top) still to be located inside the current prefix
+#pragma unroll 1
+        for (int round = 0; round < 3; ++round) {
+            const int shift = 24 - 8 * round;
+            for (int b = lane; b < 256; b += 32) hist[b] = 0;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t key = keys[i];
+                if (key != 0 && (round == 0 || (key >> (shift + 8)) == prefix)) atomicAdd(hist + ((key >> shift) & 255u), 1);
+            }
+            __syncwarp();
+            // lane l owns bins 8l .. 8l+7; suffix sums from the top bin down
+            int c8[8], mine_sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c8[j] = hist[lane * 8 + j]; mine_sum += c8[j]; }
+            int suf = mine_sum;  // inclusive suffix sum over the lanes >= this one (Hillis-Steele)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += v;
+            }
+            const int above = suf - mine_sum;  // entries in bins owned by higher lanes
+            int digit = -1, rank_in = 0;
+            if (above < want && above + mine_sum >= want) {  // the wanted rank falls into this lane's bins
+                int acc = above;
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {
+                    if (digit < 0 && acc + c8[j] >= want) { digit = lane * 8 + j; rank_in = want - acc; }
+                    acc += c8[j];
+                }
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, digit >= 0);
+            const int src = __ffs(who) - 1;
+            digit = __shfl_sync(0xffffffffu, digit, src);
+            want = __shfl_sync(0xffffffffu, rank_in, src);
+            prefix = (prefix << 8) | (uint32_t)digit;
+            __syncwarp();
+        }
+        const uint32_t tau_key = prefix << 8;  // lower edge of the bucket: <= the k-th largest key
+        tau = float_of_key(tau_key);
+        thr_key = key_of(tau - margin2);
+        if (thr_key == 0) thr_key = 1;
+    }
+    // compaction in place: chunk by chunk, every lane reads its entry before anybody writes (targets are <= sources)
+    int out = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int2 c = make_int2(-1, 0);
+        bool keep = false;
+        if (i < n) {
+            c = mine[i];
+            keep = c.x >= 0 && (dead_query ? (c.x - id_base < k) : (thr_key == 0 || keys[i] >= thr_key));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) mine[out + __popc(m & ((1u << lane) - 1u))] = c;
+        out += __popc(m);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        cand_cnt[q] = out;
+        tq[q] = dead_query ? (n > 0 ? INFINITY : -INFINITY) : (tau - margin2) * nqv;
+    }
+}
+
 struct Ws {
     float *qn, *dn, *S, *run_s, *tq;
     int *run_i, *run_cnt, *cand_cnt, *overflow;
@@ -345,6 +465,14 @@ int topk_rescore_select(const float* Q, int nq, const float* docs, int id_base, 
     tkc::topk_rescore_select_kernel<<<cdiv(nq, 4), 128, sel_smem, st>>>(Q, nq, docs, id_base, d, qn, dn, k, cand, cand_cnt, run_s, run_i, run_cnt,
                                                                        tq, margin);
     LAUNCH_CHECK("topk_rescore_select");
+    return DSSM_OK;
+}
+
+int topk_approx_select(int nq, int k, int2* cand, int* cand_cnt, const float* dn, int id_base, const float* qn, float* tq, float margin,
+                       cudaStream_t st) {
+    const size_t smem = (size_t)4 * tkc::CAP * sizeof(uint32_t) + (size_t)4 * 256 * sizeof(int);
+    tkc::topk_approx_select_kernel<<<cdiv(nq, 4), 128, smem, st>>>(nq, k, cand, cand_cnt, dn, id_base, qn, tq, 2.0f * margin);
+    LAUNCH_CHECK("topk_approx_select");
     return DSSM_OK;
 }
 
@@ -387,15 +515,12 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
     CUDA_TRY(cudaMemsetAsync(w.run_cnt, 0, (size_t)nq_pad * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nq_pad * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
-    // pass 0: exact top-k of the first `seed` docs
-    const int seed = nd < tkc::SEED_DOCS ? (int)nd : tkc::SEED_DOCS;
-    rc = topk_exact_chunk(Q, nq, docs, 0, seed, d, w.qn, w.dn, w.S, seed, id_offset, k, w.run_s, w.run_i, w.run_cnt, st);
-    if (rc != DSSM_OK) return rc;
-    // thresholds from the seed (no candidates yet)
-    rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
+    // thresholds start at -inf (empty bags): the first, short pass lets every doc through and seeds the bound
+    rc = topk_approx_select(nq, k, w.cand, w.cand_cnt, w.dn, id_offset, w.qn, w.tq, tkc::MARGIN, st);
     if (rc != DSSM_OK) return rc;
     const int n_qtiles = nq_pad / tkc::QT;
-    int64_t lo = seed, chunk = 4 * (int64_t)tkc::SEED_DOCS;
+    const int growth = k <= 160 ? 4 : 2;  // candidates per pass ~ growth * k on top of the bag: keep them inside CAP
+    int64_t lo = 0, chunk = tkc::SEED_DOCS;
     while (lo < nd) {
         const int64_t hi = (nd - lo <= chunk + chunk / 2) ? nd : lo + chunk;  // fold a short tail into the last pass
         const int tiles = (int)((hi - lo + tkc::DT - 1) / tkc::DT);
@@ -404,16 +529,19 @@ extern "C" int dssm_corpus_topk_tc(const float* Q, int32_t nq, const float* docs
         if (splits > tiles) splits = tiles;
         const int tps = (tiles + splits - 1) / splits;
         dim3 grid(n_qtiles, (tiles + tps - 1) / tps);
-        int reserve = tkc::CAP / (4 * (int)grid.y);  // unused tails of the reserved runs stay below CAP / 4 per query
+        int reserve = tkc::CAP / (8 * (int)grid.y);  // unused tails of the reserved runs stay below CAP / 8 per query
         reserve = reserve > 32 ? 32 : (reserve < 1 ? 1 : reserve);
         tkc::topk_tc_filter_kernel<<<grid, tkc::THREADS, smem, st>>>(Q, nq, docs, lo, hi, w.dn, w.tq, w.qn, id_offset, w.cand, w.cand_cnt,
                                                                      w.overflow, tps, reserve);
         LAUNCH_CHECK("topk_tc_filter");
-        rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
+        rc = topk_approx_select(nq, k, w.cand, w.cand_cnt, w.dn, id_offset, w.qn, w.tq, tkc::MARGIN, st);
         if (rc != DSSM_OK) return rc;
         lo = hi;
-        chunk *= 4;
+        chunk *= growth;
     }
+    // the bags hold every doc that can be in the exact top-k: re-score them exactly, once
+    rc = topk_rescore_select(Q, nq, docs, id_offset, d, w.qn, w.dn, k, w.cand, w.cand_cnt, w.run_s, w.run_i, w.run_cnt, w.tq, tkc::MARGIN, st);
+    if (rc != DSSM_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_scores, w.run_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(out_ids, w.run_i, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(overflow_flag, w.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));

@@ -67,7 +67,9 @@ def corpus_topk(Q: torch.Tensor, docs, k: int, id_offset: int = 0, method: str =
         flag = torch.zeros(1, dtype=torch.int32, device=Q.device)
         check(lib.dssm_corpus_topk_indexed(ptr(Q), nq, ptr(docs), ptr(index.data), nd, d, k, id_offset, ptr(s), ptr(i), ptr(flag), ptr(ws), nb,
                                            stream_ptr()))
-        fell_back = int(flag.item()) != 0
+        # overflow of a candidate list, or a query with some but fewer than k docs of finite cosine (the filters do not
+        # collect the -inf fillers behind them; a zero-norm query, all -inf, is handled by the kernels)
+        fell_back = int(flag.item()) != 0 or bool((torch.isinf(s[:, k - 1]) & ~torch.isinf(s[:, 0])).any())
         LAST_CALL.update(method="bf16", fallback=fell_back)
         if not fell_back:
             return s, i
@@ -79,7 +81,7 @@ def corpus_topk(Q: torch.Tensor, docs, k: int, id_offset: int = 0, method: str =
         i = torch.empty((nq, k), dtype=torch.int32, device=Q.device)
         flag = torch.zeros(1, dtype=torch.int32, device=Q.device)
         check(lib.dssm_corpus_topk_tc(ptr(Q), nq, ptr(docs), nd, d, k, id_offset, ptr(s), ptr(i), ptr(flag), ptr(ws), nb, stream_ptr()))
-        fell_back = int(flag.item()) != 0
+        fell_back = int(flag.item()) != 0 or bool((torch.isinf(s[:, k - 1]) & ~torch.isinf(s[:, 0])).any())
         LAST_CALL.update(method="tc", fallback=fell_back)
         if not fell_back:
             return s, i
