@@ -216,9 +216,20 @@ topk_bf16_filter_kernel(const char* __restrict__ q_img, int nq, const char* __re
                 const int ch = half * 2 + c2;
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((qt * 2 + b) * DT + ch * 32), r);
-                uint32_t keep = 0;
+                // 32 verdicts -> bit mask.  One FSET (0 / 0xffffffff, the 16-lane ALU pipe) and one multiply-add
+                // keep = 2 keep - verdict (IMAD: the FMA pipe, otherwise idle here) per score, highest column first so that
+                // column j lands on bit j.  (FSETP + SEL + IADD3, all on the ALU pipe, made the epilogue the bound of the
+                // kernel: profiles/r2_ncu_bf16_filter.txt.)
+                float k_hi = 0.f, k_lo = 0.f;  // exact: 16 bits each
 #pragma unroll
-                for (int j = 0; j < 32; ++j) keep |= (__uint_as_float(r[j]) >= t_q ? 1u : 0u) << j;
+                for (int j = 15; j >= 0; --j) {
+                    float v_hi, v_lo;
+                    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(v_hi) : "f"(__uint_as_float(r[16 + j])), "f"(t_q));
+                    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(v_lo) : "f"(__uint_as_float(r[j])), "f"(t_q));
+                    k_hi = fmaf(k_hi, 2.0f, v_hi);
+                    k_lo = fmaf(k_lo, 2.0f, v_lo);
+                }
+                uint32_t keep = ((uint32_t)k_hi << 16) | (uint32_t)k_lo;
                 const int col0 = ch * 32;
                 if (nvalid - col0 < 32) keep &= (nvalid - col0 <= 0) ? 0u : (0xffffffffu >> (32 - (nvalid - col0)));  // partial last tile
                 if (keep & 0xffffu) emit(keep & 0xffffu, r, d0 + col0);

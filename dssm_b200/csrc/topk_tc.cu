@@ -133,15 +133,24 @@ topk_tc_filter_kernel(const float* __restrict__ Q, int nq, const float* __restri
             tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(bb * DT + col0), r);
             // keep iff cos_approx >= tau - margin  <=>  dot >= (tau - margin) * ||q|| * ||d||  (norms >= 0).  Survivors
             // are rare: collect the 32 verdicts in a bit mask, branch once.
-            uint32_t keep = 0;
+            // verdicts -> bit mask with one FSET.BF (1.0f / 0.0f) and one FFMA (k = 2k + verdict, exact: 16 bits per
+            // accumulator) per score, highest column first -- see topk_bf16.cu
+            float k_hi = 0.f, k_lo = 0.f;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 nd = nrm4[(col0 >> 2) + j4];
-                keep |= (__uint_as_float(r[4 * j4 + 0]) >= t_q * nd.x ? 1u : 0u) << (4 * j4 + 0);
-                keep |= (__uint_as_float(r[4 * j4 + 1]) >= t_q * nd.y ? 1u : 0u) << (4 * j4 + 1);
-                keep |= (__uint_as_float(r[4 * j4 + 2]) >= t_q * nd.z ? 1u : 0u) << (4 * j4 + 2);
-                keep |= (__uint_as_float(r[4 * j4 + 3]) >= t_q * nd.w ? 1u : 0u) << (4 * j4 + 3);
+            for (int j4 = 3; j4 >= 0; --j4) {
+                const float4 nl = nrm4[(col0 >> 2) + j4], nh = nrm4[(col0 >> 2) + 4 + j4];
+                const float tl[4] = {t_q * nl.x, t_q * nl.y, t_q * nl.z, t_q * nl.w};
+                const float th[4] = {t_q * nh.x, t_q * nh.y, t_q * nh.z, t_q * nh.w};
+#pragma unroll
+                for (int e = 3; e >= 0; --e) {
+                    float v_hi, v_lo;
+                    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(v_hi) : "f"(__uint_as_float(r[16 + 4 * j4 + e])), "f"(th[e]));
+                    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(v_lo) : "f"(__uint_as_float(r[4 * j4 + e])), "f"(tl[e]));
+                    k_hi = fmaf(k_hi, 2.0f, v_hi);
+                    k_lo = fmaf(k_lo, 2.0f, v_lo);
+                }
             }
+            uint32_t keep = ((uint32_t)k_hi << 16) | (uint32_t)k_lo;
             if (nvalid - col0 < 32) keep &= (nvalid - col0 <= 0) ? 0u : (0xffffffffu >> (32 - (nvalid - col0)));  // partial last tile
             if (keep) {
                 // this lane has survivors in the chunk: park its 32 dots in its own shared-memory row (XOR-swizzled
@@ -315,8 +324,8 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
 // per query:
 //   key      monotone uint image of the approximate cosine; 0 = not usable for the bound (unused reserved slot, NaN, doc of
 //            zero norm -- its exact cosine is NaN = -inf whatever the filter computed)
-//   tau      a lower bound of the k-th largest usable approximate cosine: 3 rounds of an 8-bit radix select, i.e. the lower
-//            edge of the 24-bit key bucket that holds the k-th largest (-inf while fewer than k usable entries exist)
+//   tau      a lower bound of the k-th largest usable approximate cosine: 3 rounds of a 256-bucket select over the key range,
+//            i.e. the lower edge of the last bucket that holds the k-th largest (-inf while fewer than k usable entries exist)
 //   bound    k docs have exact >= approx - m >= tau - m, so the FINAL exact k-th best is >= tau - m, so any doc of the final
 //            top-k has approx >= exact - m >= tau - 2m: the bag keeps exactly the entries with approx >= tau - 2m (all of
 //            them while tau = -inf) and the next filter pass keeps docs with dot >= (tau - 2m) * ||q|| * ||d||.
@@ -344,15 +353,21 @@ topk_approx_select_kernel(int nq, int k, int2* __restrict__ cand, int* __restric
     int2* mine = cand + (size_t)q * CAP;
     const int n = min(cand_cnt[q], CAP);
     int usable = 0;
-    for (int i = lane; i < n; i += 32) {
-        const int2 c = mine[i];
-        uint32_t key = 0;
-        if (c.x >= 0) {
-            const float a = __int_as_float(c.y);
-            if (a == a && __ldg(dn + (c.x - id_base)) > 0.f) key = key_of(a);
+    for (int i0 = lane; i0 < n; i0 += 4 * 32) {  // 4 entries per lane in flight: entry, then its doc norm (two dependent loads)
+        int2 c[4];
+        float nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = (i0 + 32 * u < n) ? mine[i0 + 32 * u] : make_int2(-1, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nv[u] = c[u].x >= 0 ? __ldg(dn + (c[u].x - id_base)) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= n) continue;
+            const float a = __int_as_float(c[u].y);
+            const uint32_t key = (c[u].x >= 0 && a == a && nv[u] > 0.f) ? key_of(a) : 0u;
+            keys[i0 + 32 * u] = key;
+            usable += key != 0 ? 1 : 0;
         }
-        keys[i] = key;
-        usable += key != 0 ? 1 : 0;
     }
     usable = __reduce_add_sync(0xffffffffu, usable);
     __syncwarp();
@@ -363,16 +378,26 @@ topk_approx_select_kernel(int nq, int k, int2* __restrict__ cand, int* __restric
     const float nqv = qn[q];
     const bool dead_query = !(nqv > 0.f);
     if (!dead_query && usable >= k) {
-        uint32_t prefix = 0;
-        int want = k;  // rank (from the top) still to be located inside the current prefix
+        // range of the usable keys: the cosines of one query share their leading key bits, so the buckets of every round are
+        // laid over [lo, hi], not over fixed digit positions (with fixed digits the first round put every entry into one
+        // or two bins: a 32-way shared-memory atomic conflict per step)
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t key = keys[i];
+            if (key != 0) { lo = min(lo, key); hi = max(hi, key); }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        int want = k;  // rank (from the top) still to be located inside [lo, hi]
 #pragma unroll 1
-        for (int round = 0; round < 3; ++round) {
-            const int shift = 24 - 8 * round;
+        for (int round = 0; round < 3 && hi > lo; ++round) {
+            const uint32_t span = hi - lo;
+            const int shift = max(0, 32 - __clz(span) - 8);  // (key - lo) >> shift  in [0, 255]
             for (int b = lane; b < 256; b += 32) hist[b] = 0;
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
                 const uint32_t key = keys[i];
-                if (key != 0 && (round == 0 || (key >> (shift + 8)) == prefix)) atomicAdd(hist + ((key >> shift) & 255u), 1);
+                if (key >= lo && key <= hi && key != 0) atomicAdd(hist + ((key - lo) >> shift), 1);
             }
             __syncwarp();
             // lane l owns bins 8l .. 8l+7; suffix sums from the top bin down
@@ -399,26 +424,27 @@ topk_approx_select_kernel(int nq, int k, int2* __restrict__ cand, int* __restric
             const int src = __ffs(who) - 1;
             digit = __shfl_sync(0xffffffffu, digit, src);
             want = __shfl_sync(0xffffffffu, rank_in, src);
-            prefix = (prefix << 8) | (uint32_t)digit;
+            const uint32_t new_lo = lo + ((uint32_t)digit << shift);
+            const uint32_t width = shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u);
+            hi = min(hi, new_lo + width);
+            lo = new_lo;
             __syncwarp();
         }
-        const uint32_t tau_key = prefix << 8;  // lower edge of the bucket: <= the k-th largest key
+        const uint32_t tau_key = lo;  // lower edge of the last bucket: <= the k-th largest key
         tau = float_of_key(tau_key);
         thr_key = key_of(tau - margin2);
         if (thr_key == 0) thr_key = 1;
     }
     // compaction in place: chunk by chunk, every lane reads its entry before anybody writes (targets are <= sources)
+    // (the next chunk's entries are fetched before this chunk's survivors are written: its positions lie behind every target)
     int out = 0;
+    int2 nxt = lane < n ? mine[lane] : make_int2(-1, 0);
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
-        int2 c = make_int2(-1, 0);
-        bool keep = false;
-        if (i < n) {
-            c = mine[i];
-            keep = c.x >= 0 && (dead_query ? (c.x - id_base < k) : (thr_key == 0 || keys[i] >= thr_key));
-        }
+        const int2 c = nxt;
+        if (base + 32 < n) nxt = (i + 32 < n) ? mine[i + 32] : make_int2(-1, 0);
+        const bool keep = i < n && c.x >= 0 && (dead_query ? (c.x - id_base < k) : (thr_key == 0 || keys[i] >= thr_key));
         const unsigned m = __ballot_sync(0xffffffffu, keep);
-        __syncwarp();
         if (keep) mine[out + __popc(m & ((1u << lane) - 1u))] = c;
         out += __popc(m);
         __syncwarp();
