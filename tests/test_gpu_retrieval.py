@@ -133,3 +133,41 @@ def test_topk_bf16_index_equals_exact_path_large_and_signed():
     s4, i4 = corpus_topk(Qs, CorpusIndex(Ds), 50)
     assert retrieval.LAST_CALL["method"] == "bf16"
     assert torch.equal(i3, i4) and torch.equal(s3, s4)
+
+
+@pytest.mark.parametrize("k", [1, 300, 700])
+def test_topk_filters_other_k(k):
+    """k = 1, and k beyond 160 (chunks then grow x2, the per-query bag is larger; k = 700 may overflow the candidate lists
+    and fall back -- the result must be the exact path's either way), for both filters."""
+    from dssm_b200 import CorpusIndex, corpus_topk, retrieval
+
+    g = torch.Generator(device="cuda").manual_seed(10 + k)
+    Q = torch.relu(torch.randn((96, 128), generator=g, device="cuda"))
+    D = torch.relu(torch.randn((90000, 128), generator=g, device="cuda"))
+    D[12345] = 0
+    D[77] = D[60000]
+    s1, i1 = corpus_topk(Q, D, k, method="exact")
+    s2, i2 = corpus_topk(Q, D, k, method="tc")
+    if k <= 300:
+        assert retrieval.LAST_CALL == {"method": "tc", "fallback": False}
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    s3, i3 = corpus_topk(Q, CorpusIndex(D), k)
+    if k <= 300:
+        assert retrieval.LAST_CALL == {"method": "bf16", "fallback": False}
+    assert torch.equal(i1, i3) and torch.equal(s1, s3)
+
+
+def test_topk_filters_fewer_finite_docs_than_k():
+    """Most docs have zero norm (cosine NaN = -inf): fewer than k finite scores per query.  The filters do not collect the
+    -inf fillers, corpus_topk notices and falls back to the exact kernels: ids and scores equal the exact path."""
+    from dssm_b200 import CorpusIndex, corpus_topk, retrieval
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Q = torch.relu(torch.randn((40, 128), generator=g, device="cuda"))
+    D = torch.zeros((40000, 128), device="cuda")
+    D[::997] = torch.relu(torch.randn((len(range(0, 40000, 997)), 128), generator=g, device="cuda"))  # 41 real docs
+    s1, i1 = corpus_topk(Q, D, 100, method="exact")
+    for docs, method in ((D, "tc"), (CorpusIndex(D), "auto")):
+        s2, i2 = corpus_topk(Q, docs, 100, method=method)
+        assert retrieval.LAST_CALL["fallback"] is True
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)
