@@ -64,7 +64,7 @@ for l in range(2, len(dims)):
     class Fbn(C.Structure):
         _fields_ = [("part", C.c_void_p), ("tickets", C.c_void_p), ("fin", BnFin), ("on", C.c_int)]
 
-    if B % 128 == 0:
+    if B % 128 == 0 and R <= 128 * 64:  # the fused-moments finalize stages at most 64 M tiles
         z2 = lambda: f32(2, N)
         keep = [z2() for _ in range(9)]
         partb = torch.zeros(3 * ((R + 127) // 128) * N, device=dev)
@@ -79,7 +79,7 @@ for l in range(2, len(dims)):
     ws = torch.zeros(lib.dssm_fc_bwd_dw_workspace_bytes(R, K, N), dtype=torch.uint8, device=dev)
     dW, db = f32(K, N), f32(N)
     bench(f"fc_dw   tc      [{K}x{R}]x[{R}x{N}] (+reduce)",
-          lambda: check(lib.dssm_fc_bwd_dw(p(H), R, K, B, p(sc), p(sh), 1, p(dH), N, p(dW), None, 1, p(ws), ws.numel(), st())), 4 * R * (K + N))
+          lambda: check(lib.dssm_fc_bwd_dw(p(H), R, K, B, p(sc), p(sh), 1, p(dH), N, p(dW), None, 1 if PASSES == 3 else 2, p(ws), ws.numel(), st())), 4 * R * (K + N))
     bench(f"image build x1  [{K}x{N}]", lambda: check(lib.dssm_fc_tc_build_image(p(W), K, N, 0, R, p(imgf), st())))
 for L in sorted(set(conf.layers)):
     X, dAl = f32(R, L), f32(R, L)
