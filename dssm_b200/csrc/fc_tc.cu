@@ -24,7 +24,13 @@
 namespace dssm {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 3, THREADS = 256;
+constexpr int BM = 128, BK = 32, STAGES = 3;
+// 16 warps for gemm_tc3_kernel: ncu on the dW contraction at C3 (profiles/r2_ncu_dw_c3.txt) showed 8 warps -- two per
+// scheduler -- issuing 30 % of the time on dependent split/convert chains (stalls: wait 25 %, long scoreboard 23 %); with
+// four warps per scheduler a thread stages half as many chunks and the schedulers have twice the warps to pick from.
+constexpr int THREADS = 512;
+constexpr int A_PER = BM * BK / 4 / THREADS;                        // 16-byte A chunks per thread and k-block (2)
+constexpr int B_PER = (160 * BK / 4 + THREADS - 1) / THREADS;       // B chunks per thread at the widest tile (3, guarded)
 constexpr int MAX_BN = 160;
 constexpr int TMEM_COLS = 512;
 // The tensor core adds into its fp32 accumulator with truncation, so a long chain of MMAs into ONE accumulator
@@ -137,12 +143,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
 
     // ---- operand staging, software-pipelined one k-block ahead in registers --------------------------------
     struct Regs {
-        float4 a[4], b[5], sc[4], sh[4];
+        float4 a[A_PER], b[B_PER], sc[A_PER], sh[A_PER];
     };
     auto load_regs = [&](int kb, Regs& q) {
         const int k0 = kbeg + kb * BK;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < A_PER; ++i) {
             const int id = tid + i * THREADS;
             q.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             q.sc[i] = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
         }
         if (!MN && use_img) return;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < B_PER; ++i) {
             const int id = tid + i * THREADS;
             q.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!MN) {
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
         if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
         // prologue (BN scale/shift + activation) + hi/lo split + swizzled store
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < A_PER; ++i) {
             const int id = tid + i * THREADS;
             float4 v = q.a[i];
             bool valid;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
         }
         if (MN || !use_img) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
+            for (int i = 0; i < B_PER; ++i) {
                 const int id = tid + i * THREADS;
                 if (!MN) {
                     const int r = id >> 3, c = id & 7;
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc3_kernel(Args g) {
     const int nacc = nkb < nacc_used ? nkb : nacc_used;
     float* tile = reinterpret_cast<float*>(smem);
     const int ld = BN + 4;
-    for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
+    for (int ch = (warp >> 2); ch < nchunks; ch += THREADS / 128) {
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;  // +0.0f
