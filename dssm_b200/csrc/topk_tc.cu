@@ -309,6 +309,11 @@ topk_rescore_select_kernel(const float* __restrict__ Q, int nq, const float* __r
         run_s[(size_t)q * k + i] = ls[i];
         run_i[(size_t)q * k + i] = li[i];
     }
+    // fewer than k entries so far: the tail reads (-inf, max id), so a caller can tell an incomplete list from a full one
+    for (int i = cnt + lane; i < k; i += 32) {
+        run_s[(size_t)q * k + i] = -INFINITY;
+        run_i[(size_t)q * k + i] = 0x7fffffff;
+    }
     if (lane == 0) {
         run_cnt[q] = cnt;
         cand_cnt[q] = 0;

@@ -73,7 +73,7 @@ def corpus_topk(Q: torch.Tensor, docs, k: int, id_offset: int = 0, method: str =
         LAST_CALL.update(method="bf16", fallback=fell_back)
         if not fell_back:
             return s, i
-        method = "exact"
+        method = "exact-after-bf16"  # LAST_CALL keeps {"bf16", fallback=True}; the exact kernels below produce the result
     if method == "tc":
         nb = lib.dssm_corpus_topk_tc_workspace_bytes(nq, nd, d, k)
         ws = torch.empty(nb, dtype=torch.uint8, device=Q.device)
@@ -86,7 +86,7 @@ def corpus_topk(Q: torch.Tensor, docs, k: int, id_offset: int = 0, method: str =
         if not fell_back:
             return s, i
         # a candidate list overflowed (thresholds too loose for this data): the exact kernels always work
-    else:
+    elif method == "exact":
         LAST_CALL.update(method="exact", fallback=False)
     nb = lib.dssm_corpus_topk_workspace_bytes(nq, nd, d, k)
     ws = torch.empty(nb, dtype=torch.uint8, device=Q.device)
