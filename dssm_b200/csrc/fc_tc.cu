@@ -698,13 +698,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ws_kernel(Args g) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// "TS" variant of the warp-specialised kernel: the activation operand goes registers -> TENSOR MEMORY (tcgen05.st) and
-// the MMAs read A from TMEM, B (the weight image) from shared memory.  The SS kernel above is bound by shared-memory
-// bandwidth (160 KB per k-block -- 96 KB of operand reads by the 12 MMAs, 32 KB of hi/lo stores, 32 KB of
-// weight image); here a k-block moves 48 KB of B reads + 32 KB of image.  TMEM columns: accumulator [0, BN), A stages at
-// TS_A_COL0 + 64 st (hi: 32 columns, lo: 32 columns).  A thread must own a whole row (its warp reaches only the TMEM
-// lanes 32 (warp % 4)..+31), so it loads 64 contiguous bytes of its row per k-block instead of a coalesced 16-byte chunk.
-// Only for K <= 384 (one accumulator, as the SS kernel assumes for its short reductions).
+// TMA + TMEM variant of the warp-specialised kernel (the default for K <= 384).  The SS kernel above is bound by
+// shared-memory bandwidth (160 KB per k-block -- 96 KB of operand reads by the 12 MMAs, 32 KB of hi/lo stores,
+// 32 KB of weight image); here the A operand lives in TENSOR MEMORY: the raw fp32 activation tile is fetched by the TMA unit (cp.async.bulk.tensor.2d, one box of
+// [128 rows x 32 floats] per k-block, SWIZZLE_128B, out-of-range rows / columns zero-filled) next to the weight image tile;
+// the producers read THEIR row from shared memory (conflict-free through the swizzle), apply BN + activation, split and
+// write the A operand into tensor memory (tcgen05.st; a warp reaches only the TMEM lanes 32 (warp % 4)..+31, hence one row
+// per thread), and the MMAs read A from TMEM, B from shared memory (TS form).  No global-load instructions, no register
+// ring, and a k-block moves 112 KB through shared memory instead of 160 KB.  TMEM columns: accumulator [0, BN), A stages at
+// TS_A_COL0 + 64 st (hi: 32 columns, lo: 32 columns).  (A first TS version loaded each thread's row straight from global
+// memory -- 64 contiguous bytes per thread, 32 rows per warp instruction: ncu showed the load/store unit throttled, lg 19 %
+// of the stalls, and it was slower than the SS kernel, 18.2 vs 14.8 us; the TMA removes those instructions altogether.)
 constexpr int TS_A_COL0 = 256;
 constexpr int TMA_MAX_STAGES = 4;
 static_assert(TS_A_COL0 >= MAX_BN && TS_A_COL0 + TMA_MAX_STAGES * 64 <= TMEM_COLS, "TMEM column budget of the TS / TMA kernels");
@@ -712,341 +716,6 @@ static_assert(TS_A_COL0 >= MAX_BN && TS_A_COL0 + TMA_MAX_STAGES * 64 <= TMEM_COL
 // (measured: four stages at BN <= 128 are not faster than three -- 14.65 vs 14.17 us at C2 -- so three everywhere)
 __host__ __device__ inline int tma_stages(int BN) { return BN <= 160 ? 3 : 3; }
 
-template <int ACT>
-__global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_ts_kernel(Args g) {
-    extern __shared__ char smem_raw[];
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint64_t full_a[STAGES];
-    __shared__ uint64_t full_b[STAGES];
-    __shared__ uint64_t done_bar;
-    __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float s_scale[2][WS_MAX_K];
-    __shared__ __align__(16) float s_shift[2][WS_MAX_K];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
-    const int BN = g.BN;
-    const int b_tile_bytes = BN * BK * 4;
-    const int stage_bytes = 2 * b_tile_bytes;  // only the weight image goes through shared memory
-    char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int nkb = (g.K + BK - 1) / BK;
-    const int kpad = nkb * BK;
-
-    // Producers (warps 0-7): a thread owns ONE row of the tile -- TMEM lane 32 (warp % 4) + lane, the only lanes its warp can
-    // reach -- and 16 of the k-block's 32 columns (half = warp / 4); the first WS_PF k-blocks of loads go out before the setup.
-    const int quad = warp & 3, half = warp >> 2;
-    const int trow = quad * 32 + lane;
-    const int mrow = m0 + trow;
-    const bool okm = warp < 8 && mrow < g.M;
-    const int seg = mrow < g.Bseg ? 0 : 1;
-    const float* rowp = g.A + (size_t)(okm ? mrow : 0) * g.K + half * 16;
-    float4 buf[WS_PF][4];
-    auto load4 = [&](int kb, float4 (&q)[4]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = okm && kb < nkb && kb * BK + half * 16 + i * 4 < g.K;
-            q[i] = ok ? __ldg(reinterpret_cast<const float4*>(rowp + kb * BK) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    if (warp < 8) {
-#pragma unroll
-        for (int j = 0; j < WS_PF; ++j) load4(j, buf[j]);
-    }
-
-    if (warp == 0) tmem_alloc(&tmem_base_slot, TMEM_COLS);
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&empty_bar[s], 1);
-            mbar_init(&full_a[s], WS_PRODUCERS);
-            mbar_init(&full_b[s], 1);
-        }
-        mbar_init(&done_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < 2 * kpad; i += WS_THREADS) {  // identity prologue when there is no BN
-        const int seg = i / kpad, k = i - seg * kpad;
-        s_scale[seg][k] = (g.scale && k < g.K) ? __ldg(g.scale + seg * g.K + k) : 1.f;
-        s_shift[seg][k] = (g.scale && k < g.K) ? __ldg(g.shift + seg * g.K + k) : 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = tmem_base_slot;
-    const char* b_img = g.Bimg + (size_t)blockIdx.x * nkb * 2 * b_tile_bytes;
-
-    if (warp < 8) {
-        // ------------------------------------------------------------------ producers (256 threads, 4 chunks each)
-        for (int kb0 = 0; kb0 < nkb; kb0 += WS_PF) {
-#pragma unroll
-            for (int j = 0; j < WS_PF; ++j) {
-                const int kb = kb0 + j;
-                if (kb >= nkb) break;
-                const int st = kb % STAGES, use = kb / STAGES;
-                if (use > 0) {
-                    mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
-                    tc_fence_after();
-                }
-                const int k = kb * BK + half * 16;
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 v = buf[j][i];
-                    if (okm && k + i * 4 < g.K) {  // padding stays exactly zero
-                        const float4 sc = *reinterpret_cast<const float4*>(&s_scale[seg][k + i * 4]);
-                        const float4 sh = *reinterpret_cast<const float4*>(&s_shift[seg][k + i * 4]);
-                        v.x = act_t<ACT>(fmaf(v.x, sc.x, sh.x));
-                        v.y = act_t<ACT>(fmaf(v.y, sc.y, sh.y));
-                        v.z = act_t<ACT>(fmaf(v.z, sc.z, sh.z));
-                        v.w = act_t<ACT>(fmaf(v.w, sc.w, sh.w));
-                    }
-                    const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
-                    hi[4 * i + 0] = __float_as_uint(h0); hi[4 * i + 1] = __float_as_uint(h1);
-                    hi[4 * i + 2] = __float_as_uint(h2); hi[4 * i + 3] = __float_as_uint(h3);
-                    lo[4 * i + 0] = __float_as_uint(tf32_rna(v.x - h0)); lo[4 * i + 1] = __float_as_uint(tf32_rna(v.y - h1));
-                    lo[4 * i + 2] = __float_as_uint(tf32_rna(v.z - h2)); lo[4 * i + 3] = __float_as_uint(tf32_rna(v.w - h3));
-                }
-                // straight into tensor memory: A never touches shared memory (half of the traffic that bounded the SS kernel)
-                const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TS_A_COL0 + st * 64 + half * 16);
-                tmem_st_32x16(ta, hi);
-                if (g.passes == 3) tmem_st_32x16(ta + 32, lo);
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&full_a[st]);
-                load4(kb + WS_PF, buf[j]);  // refill the slot just consumed
-            }
-        }
-    } else if (warp == 8) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BM, BN);
-            const int nacc_used = nkb <= 12 ? 1 : NACC;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % STAGES, use = kb / STAGES;
-                mbar_wait(&full_a[st], (uint32_t)(use & 1));
-                mbar_wait(&full_b[st], (uint32_t)(use & 1));
-                tc_fence_after();
-                char* b_st = smem + st * stage_bytes;
-                const uint64_t db_hi = make_desc_k_sw128(smem_u32(b_st));
-                const uint64_t db_lo = make_desc_k_sw128(smem_u32(b_st + b_tile_bytes));
-                const uint32_t ta_hi = tmem_d + (uint32_t)(TS_A_COL0 + st * 64), ta_lo = ta_hi + 32;
-                const uint32_t acc = tmem_d;
-#pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);
-                    const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
-                    if (g.passes == 3) {
-                        mma_tf32_ts(acc, ta_hi + ks * 8, db_lo + adv, idesc, first);
-                        mma_tf32_ts(acc, ta_lo + ks * 8, db_hi + adv, idesc, 1u);
-                        mma_tf32_ts(acc, ta_hi + ks * 8, db_hi + adv, idesc, 1u);
-                    } else {
-                        mma_tf32_ts(acc, ta_hi + ks * 8, db_hi + adv, idesc, first);
-                    }
-                }
-                mma_commit(&empty_bar[st]);
-                if (kb == nkb - 1) mma_commit(&done_bar);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ B image loader (warp 9)
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % STAGES, use = kb / STAGES;
-                if (use > 0) mbar_wait(&empty_bar[st], (uint32_t)((use - 1) & 1));
-                bulk_copy_g2s(smem + st * stage_bytes, b_img + (size_t)kb * 2 * b_tile_bytes,
-                              (uint32_t)(2 * b_tile_bytes), &full_b[st]);
-            }
-        }
-    }
-    __syncwarp();
-    if (warp < 8) {
-        mbar_wait(&done_bar, 0);
-        tc_fence_after();
-        // ---- epilogue (warps 0-7): TMEM -> registers -> (+bias) -> global.  Warp w owns TMEM lanes 32*(w%4)..+31 ----
-        const int lane_grp = warp & 3;
-        const int row = m0 + lane_grp * 32 + lane;
-        const int nchunks = BN / 32;
-        const int nacc_e = 1;  // K <= 384 on this path: one accumulator
-        // scratch for the fused column moments: the pipeline stages are free once done_bar has completed
-        float* sc_n = reinterpret_cast<float*>(smem);
-        float* sc_mu = sc_n + 4 * MAX_BN;
-        float* sc_m2 = sc_mu + 4 * MAX_BN;
-        if (!g.fbn.on) {
-            // Coalesced epilogue: TMEM -> registers -> the (now free) pipeline shared memory as a [128][BN + 4] fp32 tile ->
-            // full rows to global, a warp writing 512 contiguous bytes per instruction.  Writing straight from the TMEM
-            // layout (a lane = a row) made every 128-bit store instruction touch 32 different rows, 16 bytes each: ~2 us per
-            // 32-column chunk (measured with in-kernel timestamps: 4.1 us of a 17 us tile at BN = 128).
-            float* tile = reinterpret_cast<float*>(smem);
-            const int ld = BN + 4;
-            for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
-                for (int a = 1; a < nacc_e; ++a) {
-                    uint32_t t[32];
-                    tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
-                }
-                float* dst = tile + (size_t)(lane_grp * 32 + lane) * ld + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                                                      __uint_as_float(r[j + 3]));
-            }
-            tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
-            const int n4 = BN / 4;                          // float4 columns of the tile (BN is a multiple of 32)
-            const int nvalid = min(BN, g.N - n0);           // N is a multiple of 4 on this path
-            for (int c4 = lane; c4 < n4; c4 += 32) {
-                if (c4 * 4 >= nvalid) continue;
-                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.bias) bz = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c4 * 4));
-                for (int rr = warp; rr < BM; rr += 8) {
-                    if (m0 + rr >= g.M) break;
-                    float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c4 * 4);
-                    o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
-                    *reinterpret_cast<float4*>(g.D + (size_t)(m0 + rr) * g.N + n0 + c4 * 4) = o;
-                }
-            }
-        } else
-        for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), r);
-            for (int a = 1; a < nacc_e; ++a) {
-                uint32_t t[32];
-                tmem_ld_32x32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * MAX_BN + ch * 32), t);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
-            }
-            const int nb = n0 + ch * 32;
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]) + ((g.bias && nb + j < g.N) ? __ldg(g.bias + nb + j) : 0.f);
-            if (row < g.M) {
-                float* out = g.D + (size_t)row * g.N + nb;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (nb + j + 3 < g.N) {
-                        *reinterpret_cast<float4*>(out + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (nb + j + q < g.N) out[j + q] = o[j + q];
-                    }
-                }
-            }
-            if (g.fbn.on && !(g.fbn.on & 8)) {
-                // (count, mean, M2) of this warp's 32 rows for the 32 columns of the chunk: shifted by the warp's first row
-                // (no E[x^2] - E[x]^2 cancellation), then a butterfly transpose-reduce -- 31 shuffles per statistic leave
-                // lane j with the totals of column j
-                const bool valid = row < g.M;
-                const int n_w = __popc(__ballot_sync(0xffffffffu, valid));
-                float sq[32], kmine = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float kj = __shfl_sync(0xffffffffu, o[j], 0);
-                    if (lane == j) kmine = kj;
-                    const float d = valid ? o[j] - kj : 0.f;
-                    o[j] = d;
-                    sq[j] = d * d;
-                }
-#define XSTEP(OFF, NN)                                                            \
-    _Pragma("unroll") for (int i = 0; i < NN; ++i) {                              \
-        const bool up = (lane & OFF) != 0;                                        \
-        const float send_s = up ? o[i] : o[i + NN], keep_s = up ? o[i + NN] : o[i]; \
-        const float send_q = up ? sq[i] : sq[i + NN], keep_q = up ? sq[i + NN] : sq[i]; \
-        o[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, OFF);                \
-        sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, OFF);               \
-    }
-                XSTEP(16, 16) XSTEP(8, 8) XSTEP(4, 4) XSTEP(2, 2) XSTEP(1, 1)
-#undef XSTEP
-                const int cidx = lane_grp * MAX_BN + ch * 32 + lane;
-                if (n_w > 0) {
-                    const float md = o[0] / (float)n_w;
-                    sc_n[cidx] = (float)n_w;
-                    sc_mu[cidx] = kmine + md;
-                    sc_m2[cidx] = fmaxf(sq[0] - o[0] * md, 0.f);
-                } else {
-                    sc_n[cidx] = 0.f;
-                    sc_mu[cidx] = 0.f;
-                    sc_m2[cidx] = 0.f;
-                }
-            }
-        }
-        if (g.fbn.on && !(g.fbn.on & 4)) {
-            const int n_mtiles = gridDim.y;
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
-            if (tid < BN && n0 + tid < g.N) {  // the tile's triple per column: lane groups merged in row order
-                float cn = 0.f, mu = 0.f, m2 = 0.f;
-#pragma unroll
-                for (int lg = 0; lg < 4; ++lg) chan_merge(cn, mu, m2, sc_n[lg * MAX_BN + tid], sc_mu[lg * MAX_BN + tid], sc_m2[lg * MAX_BN + tid]);
-                float* part = g.fbn.part;
-                part[((size_t)0 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = cn;
-                part[((size_t)1 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = mu;
-                part[((size_t)2 * n_mtiles + blockIdx.y) * g.N + n0 + tid] = m2;
-            }
-            // "last CTA of this N tile finalizes" (same ticket scheme as bn.cu)
-            __shared__ int s_last;
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid == 0) {
-                const int prev = atomicAdd(g.fbn.tickets + blockIdx.x, 1);
-                s_last = prev == n_mtiles - 1;
-                if (s_last) g.fbn.tickets[blockIdx.x] = 0;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (s_last && !(g.fbn.on & 2)) {
-                // Finalize this N tile's columns.  The partials were written by other SMs, so every read is an L2 round
-                // trip: a thread-per-column serial merge over the M tiles costs one round trip per tile, and staging through
-                // a generic-pointer smem store per load serialises the same way (measured: +14..29 us per GEMM).  So: the 256
-                // threads pull [3][M tiles][BN] into the (now free) pipeline smem with 128-bit loads, STAGE_MLP of them in
-                // flight per thread before the first store, then one thread per (column, instance) merges its tiles in
-                // ascending order from shared memory -- fixed order, deterministic.  (n_mtiles <= 64: caller's contract.)
-                __threadfence();
-                const int nq = g.fbn.fin.nq_chunks;
-                float4* st4 = reinterpret_cast<float4*>(smem);
-                const float* st = reinterpret_cast<const float*>(smem);
-                const int bn4 = BN / 4;
-                const int total4 = 3 * n_mtiles * bn4;
-                const float* part = g.fbn.part;
-                constexpr int STAGE_MLP = 8;
-                for (int e0 = tid; e0 < total4; e0 += 256 * STAGE_MLP) {
-                    float4 v[STAGE_MLP];
-#pragma unroll
-                    for (int u = 0; u < STAGE_MLP; ++u) {
-                        const int e = e0 + u * 256;
-                        const int pc = e / bn4, c4 = e - pc * bn4;
-                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e < total4 && n0 + c4 * 4 < g.N) v[u] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)pc * g.N + n0 + c4 * 4));
-                    }
-#pragma unroll
-                    for (int u = 0; u < STAGE_MLP; ++u)
-                        if (e0 + u * 256 < total4) st4[e0 + u * 256] = v[u];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int pr = tid; pr < 2 * BN; pr += 256) {
-                    const int seg = pr / BN, cl = pr - seg * BN, col = n0 + cl;
-                    const int c0 = seg == 0 ? 0 : nq, c1 = seg == 0 ? nq : n_mtiles;
-                    if (col >= g.N || c0 >= c1) continue;
-                    float cn = 0.f, mu = 0.f, m2 = 0.f;
-                    for (int c = c0; c < c1; ++c)
-                        chan_merge(cn, mu, m2, st[(0 * n_mtiles + c) * BN + cl], st[(1 * n_mtiles + c) * BN + cl], st[(2 * n_mtiles + c) * BN + cl]);
-                    bn_finalize_column(g.fbn.fin, seg * g.N + col, mu, m2 / cn);  // biased variance (tf.nn.moments)
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// TMA + TMEM variant: the raw fp32 activation tile is fetched by the TMA unit (cp.async.bulk.tensor.2d, one box of
-// [128 rows x 32 floats] per k-block, SWIZZLE_128B, out-of-range rows / columns zero-filled) next to the weight image tile;
-// the producers read THEIR row from shared memory (conflict-free through the swizzle), apply BN + activation, split and
-// write the A operand into tensor memory.  No global-load instructions, no register ring, and a k-block moves 112 KB
-// through shared memory instead of 160 KB (the SS kernel) -- the row-per-thread global loads of gemm_tc3_ts_kernel
-// throttled the load/store unit (ncu: lg_throttle 19 %, 18.2 vs 14.8 us per GEMM).
 template <int ACT>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_tma_kernel(Args g, const __grid_constant__ CUtensorMap tmap_a) {
     extern __shared__ char smem_raw[];
@@ -1141,7 +810,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc3_tma_kernel(Args g, con
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, BN);
-            const int nacc_used = nkb <= 12 ? 1 : NACC;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % nst, use = kb / nst;
                 mbar_wait(&full_a[st], (uint32_t)(use & 1));
@@ -1415,8 +1083,8 @@ static int pick_bn(int N, int M) {
     return bn > MAX_BN ? MAX_BN : bn;
 }
 
-// which kernel feeds the A operand of the K-major contractions: 0 = SS (shared memory), 1 = TS with row-per-thread global
-// loads, 2 = TMA + TMEM
+// which kernel runs the K-major contractions: 2 (default) = TMA + TMEM (A operand in tensor memory), 0 = SS (both operands
+// in shared memory; also used for K > 384 and for the fused-BN-moments epilogue)
 static int ts_mode() {
     const char* e = getenv("DSSM_GEMM_TS");
     return e ? atoi(e) : 2;  // default: TMA + TMEM (C2: -0.7 / -0.9 us on the 300-wide GEMMs, C3: -13 % / -17 %)
@@ -1459,9 +1127,6 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ws_kernel<DSSM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ts_kernel<DSSM_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ts_kernel<DSSM_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_ts_kernel<DSSM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_tma_kernel<DSSM_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_tma_kernel<DSSM_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc3_tma_kernel<DSSM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_BN)));
@@ -1469,7 +1134,7 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
     if (splits > 0) {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM), splits);
         gemm_tc3_kernel<true><<<grid, THREADS, smem_bytes(a.BN), st>>>(a);
-    } else if (a.Bimg && a.K <= 384 && !a.fbn.on && ts_mode() == 2) {
+    } else if (a.Bimg && a.K <= 384 && !a.fbn.on && ts_mode() == 2 && encode_tiled_fn() != nullptr) {
         alignas(64) CUtensorMap tm;
         const int rc = make_tmap_a(a.A, a.M, a.K, &tm);
         if (rc != DSSM_OK) return rc;
@@ -1481,12 +1146,6 @@ static int launch(const Args& a, cudaStream_t st, int splits = 0) {
         if (a.act == DSSM_ACT_RELU) gemm_tc3_tma_kernel<DSSM_ACT_RELU><<<grid, WS_THREADS, sm, st>>>(a, tm);
         else if (a.act == DSSM_ACT_TANH) gemm_tc3_tma_kernel<DSSM_ACT_TANH><<<grid, WS_THREADS, sm, st>>>(a, tm);
         else gemm_tc3_tma_kernel<DSSM_ACT_NONE><<<grid, WS_THREADS, sm, st>>>(a, tm);
-    } else if (a.Bimg && a.K <= 384 && !a.fbn.on && ts_mode() == 1) {
-        // A operand through tensor memory instead of shared memory (DSSM_GEMM_TS=0 selects the SS kernel)
-        dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
-        if (a.act == DSSM_ACT_RELU) gemm_tc3_ts_kernel<DSSM_ACT_RELU><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
-        else if (a.act == DSSM_ACT_TANH) gemm_tc3_ts_kernel<DSSM_ACT_TANH><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
-        else gemm_tc3_ts_kernel<DSSM_ACT_NONE><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
     } else if (a.Bimg && a.K <= WS_MAX_K - BK) {
         dim3 grid(cdiv(a.N, a.BN), cdiv(a.M, BM));
         if (a.act == DSSM_ACT_RELU) gemm_tc3_ws_kernel<DSSM_ACT_RELU><<<grid, WS_THREADS, smem_bytes(a.BN), st>>>(a);
