@@ -14,9 +14,16 @@
 // (make_b_image_kernel) that each CTA pulls into shared memory with cp.async.bulk + mbarrier complete_tx, so the
 // threads only stage the activation operand.
 //
-// CTA = 256 threads, one 128 x BN output tile, BK = 32 fp32 (one 128-byte swizzle row) per stage, 3 stages.
-// All threads stage operands (global -> registers -> split -> 128B-swizzled smem), thread 0 issues the MMAs,
-// tcgen05.commit releases a stage through an mbarrier, and the 8 warps drain TMEM with tcgen05.ld.
+// Kernels in this file (one 128 x BN output tile per CTA, BK = 32 fp32 per k-block, 3 stages):
+//   gemm_tc3_tma_kernel  K-major, default: raw activation tiles by TMA (cp.async.bulk.tensor.2d), producers read their row
+//                        from shared memory, A operand written into TENSOR MEMORY (tcgen05.st), TS-form MMAs
+//   gemm_tc3_ws_kernel   K-major, SS form: warps 0-7 stage A (global -> registers -> split -> swizzled smem), warp 8 issues
+//                        the MMAs, warp 9 streams the weight image; fallback (K > 384, fused BN moments, DSSM_GEMM_TS=0)
+//   gemm_tc3_kernel<MN>  MN = true: the dW contraction, both operands MN-major as they lie in memory, reduction over the
+//                        rows split over blockIdx.z; MN = false: K-major without a weight image (generic entry points).
+//                        16 warps stage both operands, thread 0 issues the MMAs after a CTA barrier
+// In all of them tcgen05.commit releases a stage through an mbarrier and the epilogue goes TMEM -> registers -> shared
+// memory -> full rows to global.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "bn_common.cuh"
