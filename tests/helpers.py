@@ -106,6 +106,9 @@ def assert_update_close(got, ref, init, use_bn, what="", l2_tol=2e-2):
         upd = np.linalg.norm((r - i0).ravel())
         if upd > 0:
             rel = np.linalg.norm((g - r).ravel()) / upd
+            if os.environ.get("DSSM_TEST_REPORT"):  # measured values behind the tolerances (appended to the named file)
+                with open(os.environ["DSSM_TEST_REPORT"], "a") as f:
+                    f.write(f"{what} {k} rel_l2_of_update {rel:.3e} (tol {l2_tol})\n")
             assert rel <= l2_tol, f"{what} {k}: update differs by {rel:.2e} in relative L2"
 
 

@@ -95,7 +95,8 @@ def test_two_gpu_data_parallel_matches_dp_oracle(tmp_path, use_graph, comm):
         dp.train_step(mats)
     assert abs(got["losses"][0] - ref_losses[0]) <= 1e-5 * abs(ref_losses[0])
     assert abs(got["losses"][1] - ref_losses[1]) <= 2e-3 * abs(ref_losses[1])
-    assert_update_close({k: got["p_" + k] for k in params}, dp.model.p, params, conf.use_bn, "dp params", l2_tol=0.1)
+    # measured maximum (DSSM_TEST_REPORT, round 2): 5.6e-2 on bn1_q_beta, 1.3e-2 on W1; tolerance = measured + 40 %
+    assert_update_close({k: got["p_" + k] for k in params}, dp.model.p, params, conf.use_bn, "dp params", l2_tol=0.08)
     for k, v in dp.model.ema.items():
         if k.endswith("ema_var"):
             assert_close(got["e_" + k], v, 2e-2, f"dp ema {k}")
@@ -227,7 +228,8 @@ def test_two_gpu_syncbn_reproduces_the_single_process_reference(tmp_path, comm):
         else:
             orc.adam_update(orc.backward(cache))
     for r in range(2):
-        assert_update_close({k: got[r]["p_" + k] for k in params}, orc.p, params, conf.use_bn, f"syncbn params rank {r}", l2_tol=0.1)
+        # measured maximum (DSSM_TEST_REPORT, round 2): 1.3e-2; tolerance = measured x 2.3
+        assert_update_close({k: got[r]["p_" + k] for k in params}, orc.p, params, conf.use_bn, f"syncbn params rank {r}", l2_tol=0.03)
     for k in params:
         assert np.array_equal(got[0]["p_" + k], got[1]["p_" + k]), f"replicas differ in {k}"
     for k, v in orc.ema.items():

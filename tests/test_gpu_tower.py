@@ -162,7 +162,9 @@ def test_tower_against_live_oracle(name, gemm_mode):
     lo = orc.train_step(batches[1].to_scipy())
     lg = t.train_step(t.to_device(batches[1])).item()
     assert abs(lg - lo) <= 2e-3 * abs(lo)  # one violent Adam step (lr*sign(g) on every touched weight) amplifies noise
-    assert_update_close(t.export_params(), orc.p, params, conf.use_bn, "after 2 steps", l2_tol=0.15)
+    # measured maximum over the parametrisations (DSSM_TEST_REPORT, round 2): 0.103 -- on a BN beta vector, where a handful of
+    # noise-gradient entries whose first Adam step is +-lr weigh most; W1..W3 stay below 2e-2.  Tolerance = measured + 25 %.
+    assert_update_close(t.export_params(), orc.p, params, conf.use_bn, "after 2 steps", l2_tol=0.13)
     for k, v in t.export_ema().items():
         if k.endswith("ema_var"):
             assert_close(v, orc.ema[k], 2e-2, f"ema {k}")  # after a violent first Adam step (see above)
